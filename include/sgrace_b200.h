@@ -1,0 +1,188 @@
+/*
+ * sgrace_b200.h -- C ABI of libsgrace_b200.so, the B200 (sm_100a) replacement for the SGRACE
+ * FPGA layer accelerator `mmult_top`.
+ *
+ * The reference reaches its accelerator through PYNQ: an AXI-Lite register file
+ * (`my_ip.register_map.<name> = v`), physically contiguous DMA buffers (`allocate()` ->
+ * `.physical_address`) and the AP_START / AP_DONE handshake.  This header is that boundary:
+ *
+ *   reference interface                                     entry point here
+ *   ------------------------------------------------------  ---------------------------
+ *   Overlay("gat_all_unsigned.bit"); ol.mmult_top_0         sgrace_create / sgrace_destroy
+ *     (demo/sgrace_lib/sgrace.py:1274-1278,
+ *      jupyter/molecule_gcn/Graph_Classification.ipynb cell 11:4-5)
+ *   pynq.allocate(n, dtype) / buf.physical_address          sgrace_alloc
+ *     (sgrace.py:1552-1642, notebook cell 11:7-20)
+ *   buf.freebuffer()  (jupyter/test/mmult-master.ipynb 50)  sgrace_free
+ *   register_map.<reg> = value                              sgrace_write_reg
+ *     (sgrace.py:334-420, 1744-1891; kernelMatrixmult_all.cpp:3777-3861;
+ *      offsets: demo/zcu104/gat_all_unsigned.hwh:16153-18563)
+ *   int(register_map.max_fea)  (sgrace.py:506)              sgrace_read_reg
+ *   register_map.CTRL.AP_START = 1  (sgrace.py:488)         sgrace_start
+ *   register_map.CTRL.AP_DONE poll  (sgrace.py:489-491)     sgrace_done / sgrace_wait
+ *   HLS build-time #defines (src/matrix_mult.h:80-195)      sgrace_set_option
+ *   mmult_top(...) argument list                            sgrace_layer_run (device pointers,
+ *     (kernelMatrixmult_all.cpp:3762-3774)                   no register file, no staging)
+ *
+ * All functions return 0 on success, a negative SGRACE_E* code otherwise, and never throw.
+ * One handle owns one CUDA stream; calls on a handle must be serialised by the caller;
+ * different handles may be used from different threads / ranks.
+ */
+#ifndef SGRACE_B200_H
+#define SGRACE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sgrace_handle sgrace_handle;
+
+enum {
+    SGRACE_OK = 0,
+    SGRACE_EINVAL = -1,     /* bad argument / inconsistent registers               */
+    SGRACE_ENOMEM = -2,
+    SGRACE_ECUDA = -3,      /* CUDA error, text in sgrace_last_error               */
+    SGRACE_EUNSUPPORTED = -4,
+    SGRACE_EBOUNDS = -5     /* rowPtr not monotonic / column index out of range    */
+};
+
+/* ---- arithmetic modes (what matrix_mult.h:69-151 selects at build time) ---- */
+enum {
+    SGRACE_MODE_F32_FAST = 0,   /* float32, FMA, row order; within 1e-5 of FLOAT C-sim     */
+    SGRACE_MODE_F32_CSIM = 1,   /* FLOAT build: bit-exact C-simulation accumulate order     */
+    SGRACE_MODE_F16_CSIM = 2,   /* HALF build (matrix_mult.h:80): bit-exact, buffers fp16   */
+    SGRACE_MODE_FIX16_CSIM = 3, /* EIGHTBIT build ap_fixed<16,2>: bit-exact, buffers int16  */
+    SGRACE_MODE_FULL = 4        /* closed full design (quantise/GAT), float32 buffers,
+                                   semantics of sgrace.py:563-681                          */
+};
+
+/* ---- options: the reference's build-time knobs as runtime fields ---- */
+enum {
+    SGRACE_OPT_MODE = 1,            /* SGRACE_MODE_*                                        */
+    SGRACE_OPT_SPMM_BLOCK = 2,      /* SPMM_BLOCK        matrix_mult.h:169 (csim modes)     */
+    SGRACE_OPT_LAT_FEA = 3,         /* FTYPE_LATENCY_FEA matrix_mult.h:118,138,150          */
+    SGRACE_OPT_LAT_ADJ = 4,         /* FTYPE_LATENCY_ADJ                                    */
+    SGRACE_OPT_FEA_THREADS = 5,     /* FEA_THREADS       matrix_mult.h:166                  */
+    SGRACE_OPT_ADJ_THREADS = 6,     /* ADJ_THREADS       matrix_mult.h:167                  */
+    SGRACE_OPT_USE_SBLOCKS = 7,     /* USE_SBLOCKS       matrix_mult.h:170                  */
+    SGRACE_OPT_INDEX_FORMAT = 8,    /* 0: rowPtr buffers hold CSR pointers (open design)
+                                       1: rowPtr buffers hold sorted COO row indices and
+                                          nnz_fea1 / nnz_adj1 give the counts (full design,
+                                          sgrace.py:1221-1249)                              */
+    SGRACE_OPT_QBITS = 9,           /* config.w_qbits: 8,4,2,1; 0 = no quantisation (FULL)  */
+    SGRACE_OPT_STAGING = 10,        /* 1: buffers from sgrace_alloc are copied host->device
+                                          before and device->host after every start (PYNQ
+                                          shared-memory behaviour); 0: device-resident      */
+    SGRACE_OPT_LONG_ROW = 11,       /* rows with more non-zeros go to the CTA-per-row kernel */
+    SGRACE_OPT_LEAKY_ALPHA_BITS = 12, /* float bits of the GAT LeakyReLU slope (default 0.2) */
+    SGRACE_OPT_VALIDATE = 13,       /* 1: check CSR structure on the host mirror at start   */
+    SGRACE_OPT_DENSE_TC = 14        /* 1: allow the tcgen05 path for wide dense FEA (FAST)  */
+};
+
+/* ---- register offsets: the AXI-Lite map of gat_all_unsigned.hwh:16153-18563 ---- */
+enum {
+    SGRACE_REG_CTRL = 0x00,         /* bit0 AP_START, bit1 AP_DONE, bit2 AP_IDLE, bit3 AP_READY */
+    SGRACE_REG_LOAD_WEIGHTS = 0x10, SGRACE_REG_BETA_QU = 0x18, SGRACE_REG_F_ALIGN = 0x20,
+    SGRACE_REG_QSCALE_ADJ = 0x28, SGRACE_REG_QSCALE_FEA = 0x30, SGRACE_REG_QSCALE_W = 0x38,
+    SGRACE_REG_DEQ_FACTOR = 0x40, SGRACE_REG_STREAM_MODE = 0x48, SGRACE_REG_GAT_MODE = 0x50,
+    SGRACE_REG_GEMM_MODE = 0x58, SGRACE_REG_RELU = 0x60, SGRACE_REG_SCALE_FEA = 0x68,
+    SGRACE_REG_MAX_FEA = 0x70,      /* read-only */
+    SGRACE_REG_LAYER_COUNT = 0x80, SGRACE_REG_QUANTIZED_MULTIPLIER = 0x88,
+    SGRACE_REG_SHIFT = 0x90, SGRACE_REG_BIAS = 0x9c, SGRACE_REG_BIAS_COUNT = 0xa8,
+    SGRACE_REG_PROFILING = 0xb0, SGRACE_REG_ZP_LHS = 0xbc, SGRACE_REG_ZP_RHS = 0xc4,
+    SGRACE_REG_ZP_DST = 0xcc, SGRACE_REG_CLAMP_MAX = 0xd4, SGRACE_REG_CLAMP_MIN = 0xdc,
+    SGRACE_REG_N_ADJ = 0xe4, SGRACE_REG_M_ADJ = 0xec, SGRACE_REG_M_FEA = 0xf4, SGRACE_REG_P_W = 0xfc,
+    SGRACE_REG_B = 0x104,           /* pointer registers: <name>_offset_1 (low 32 bits) at the  */
+    SGRACE_REG_D1 = 0x110, SGRACE_REG_D2 = 0x11c, SGRACE_REG_D3 = 0x128, SGRACE_REG_D4 = 0x134,
+    SGRACE_REG_E1 = 0x140, SGRACE_REG_S1 = 0x14c, SGRACE_REG_ATE_M = 0x158, /* listed offset,    */
+    SGRACE_REG_ARRAY_C_ADJUST = 0x164,                      /* <name>_offset_2 (high) at +4    */
+    SGRACE_REG_NNZ_FEA1 = 0x16c, SGRACE_REG_NNZ_FEA2 = 0x174, SGRACE_REG_NNZ_FEA3 = 0x17c,
+    SGRACE_REG_NNZ_FEA4 = 0x184,
+    SGRACE_REG_ROWPTR_FEA1 = 0x18c, SGRACE_REG_ROWPTR_FEA2 = 0x198, SGRACE_REG_ROWPTR_FEA3 = 0x1a4,
+    SGRACE_REG_ROWPTR_FEA4 = 0x1b0,
+    SGRACE_REG_COLIDX_FEA1 = 0x1bc, SGRACE_REG_COLIDX_FEA2 = 0x1c8, SGRACE_REG_COLIDX_FEA3 = 0x1d4,
+    SGRACE_REG_COLIDX_FEA4 = 0x1e0,
+    SGRACE_REG_VALUES_FEA1 = 0x1ec, SGRACE_REG_VALUES_FEA2 = 0x1f8, SGRACE_REG_VALUES_FEA3 = 0x204,
+    SGRACE_REG_VALUES_FEA4 = 0x210,
+    SGRACE_REG_NNZ_ADJ1 = 0x21c, SGRACE_REG_NNZ_ADJ2 = 0x224, SGRACE_REG_NNZ_ADJ3 = 0x22c,
+    SGRACE_REG_NNZ_ADJ4 = 0x234,
+    SGRACE_REG_ROWPTR_ADJ1 = 0x23c, SGRACE_REG_ROWPTR_ADJ2 = 0x248, SGRACE_REG_ROWPTR_ADJ3 = 0x254,
+    SGRACE_REG_ROWPTR_ADJ4 = 0x260,
+    SGRACE_REG_COLIDX_ADJ1 = 0x26c, SGRACE_REG_COLIDX_ADJ2 = 0x278, SGRACE_REG_COLIDX_ADJ3 = 0x284,
+    SGRACE_REG_COLIDX_ADJ4 = 0x290,
+    SGRACE_REG_VALUES_ADJ1 = 0x29c, SGRACE_REG_VALUES_ADJ2 = 0x2a8, SGRACE_REG_VALUES_ADJ3 = 0x2b4,
+    SGRACE_REG_VALUES_ADJ4 = 0x2c0,
+    /* open-design-only pointer register (mmult-master.ipynb 31:34); accepted, unused
+     * (the requantiser `scale()` is dead code, kernelMatrixmult_all.cpp:3485) */
+    SGRACE_REG_QUANTIZED_MULTIPLIER_PTR = 0x400,
+    SGRACE_REG_FILE_BYTES = 0x480
+};
+
+/* ---- lifecycle ---- */
+int sgrace_create(int device, sgrace_handle** out);
+int sgrace_destroy(sgrace_handle* h);
+const char* sgrace_last_error(sgrace_handle* h);
+const char* sgrace_version(void);
+
+/* ---- buffers (pynq.allocate look-alike): pinned host mirror + device buffer ---- */
+int sgrace_alloc(sgrace_handle* h, size_t bytes, void** host_ptr, uint64_t* device_addr);
+int sgrace_free(sgrace_handle* h, uint64_t device_addr);
+/* explicit copies between a mirror and its device buffer (offsets relative to device_addr) */
+int sgrace_sync_to_device(sgrace_handle* h, uint64_t device_addr, size_t bytes);
+int sgrace_sync_from_device(sgrace_handle* h, uint64_t device_addr, size_t bytes);
+
+/* ---- register file ---- */
+int sgrace_write_reg(sgrace_handle* h, uint32_t offset, uint32_t value);
+int sgrace_read_reg(sgrace_handle* h, uint32_t offset, uint32_t* value);
+int sgrace_write_reg64(sgrace_handle* h, uint32_t offset, uint64_t value); /* _offset_1 + _offset_2 */
+int sgrace_reg_offset(const char* name, uint32_t* offset);                 /* "N_adj" -> 0xe4 ...   */
+
+int sgrace_set_option(sgrace_handle* h, int key, int64_t value);
+int sgrace_get_option(sgrace_handle* h, int key, int64_t* value);
+int sgrace_set_stream(sgrace_handle* h, void* cuda_stream);                /* NULL: own stream      */
+
+/* ---- run: one layer per start, as one AP_START pulse does ---- */
+int sgrace_start(sgrace_handle* h);
+int sgrace_done(sgrace_handle* h, int* done);   /* non-blocking */
+int sgrace_wait(sgrace_handle* h);              /* blocks; returns the layer's status */
+/* per-stage device times of the last completed layer, milliseconds (after sgrace_wait) */
+int sgrace_stage_times(sgrace_handle* h, float* fea_ms, float* adj_ms, float* total_ms);
+
+/* ---- direct call with device pointers: the argument list of mmult_top ---- */
+typedef struct {
+    int32_t gemm_mode;          /* 0 sparse X, 1 dense X (2 = hardware backward: unsupported) */
+    int32_t relu;
+    int32_t gat_mode;           /* FULL mode only */
+    int32_t N_adj, M_adj, M_fea, P_w;
+    int32_t nnz_fea, nnz_adj;   /* required for INDEX_FORMAT 1; else may be 0 (= unknown)    */
+    /* FULL-mode per-layer constants (register semantics, sgrace.py:334-365, 476) */
+    int32_t scale_fea;
+    int32_t internal_quantization;
+    float   qscale_fea, qscale_w, qscale_adj;   /* 1/s as float32 */
+    float   deq_factor;
+    /* device pointers */
+    const int32_t* rowPtr_fea; const int32_t* columnIndex_fea; const void* values_fea;
+    const int32_t* rowPtr_adj; const int32_t* columnIndex_adj; const void* values_adj;
+    const void* B;              /* W transposed, P_w x M_fea */
+    const float* attention;     /* 2*P_w, FULL + gat_mode */
+    void* D;                    /* N_adj x P_w */
+    float* E; float* S;         /* nnz_adj each, FULL + gat_mode, may be NULL */
+    void* XW;                   /* optional: caller-provided N_adj x P_w intermediate
+                                   (the PIPO tile); NULL = library scratch */
+} sgrace_layer_desc;
+
+int sgrace_layer_run(sgrace_handle* h, const sgrace_layer_desc* d);        /* async on the stream */
+/* stages separately, for multi-GPU row partitioning (all-gather of XW between them) */
+int sgrace_fea_run(sgrace_handle* h, const sgrace_layer_desc* d, void* XW_out);
+int sgrace_adj_run(sgrace_handle* h, const sgrace_layer_desc* d, const void* XW_in, int32_t xw_rows);
+
+/* number of this library's kernels launched on the handle since creation (bench evidence) */
+int sgrace_launch_count(sgrace_handle* h, uint64_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

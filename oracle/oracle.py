@@ -39,7 +39,7 @@ class _QLayer(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "gemm_mode", "gat_mode", "relu", "qbits", "N_adj", "M_fea", "P_w", "scale_fea",
         "internal_quantization")] + [
-        ("f_s", C.c_float), ("w_s", C.c_float), ("a_s", C.c_float),
+        ("qscale_fea", C.c_float), ("qscale_w", C.c_float), ("qscale_adj", C.c_float),
         ("f_z", C.c_int), ("w_z", C.c_int), ("a_z", C.c_int),
         ("deq_o", C.c_float), ("alpha", C.c_float)] + [
         (n, C.c_void_p) for n in (
@@ -182,11 +182,6 @@ def layer(*, dtype, N, M_fea, P, adj, B, fea=None, x_dense=None, relu=0, spmm_bl
     return (D, XW) if return_xw else D
 
 
-def make_layer_desc(**kw):
-    """Build a reusable descriptor (+ keep-alive list) for sgrace_oracle_layer_batch."""
-    raise NotImplementedError
-
-
 def layer_batch(descs, threads):
     arr = (_Layer * len(descs))(*descs)
     rc = lib().sgrace_oracle_layer_batch(arr, len(descs), int(threads))
@@ -207,7 +202,9 @@ def qlayer(*, N, M_fea, P, adj, B, fea=None, x_dense=None, attention=None, relu=
     if qbits:
         d.scale_fea = consts["scale_fea"]
         d.internal_quantization = consts["internal_quantization"]
-        d.f_s, d.w_s, d.a_s = consts["f_s"], consts["w_s"], consts["a_s"]
+        d.qscale_fea = float(np.float32(1.0 / consts["f_s"]))
+        d.qscale_w = float(np.float32(1.0 / consts["w_s"]))
+        d.qscale_adj = float(np.float32(1.0 / consts["a_s"]))
         d.f_z, d.w_z, d.a_z = consts["f_z"], consts["w_z"], consts["a_z"]
         d.deq_o = consts["deq_o"]
     d.alpha = alpha

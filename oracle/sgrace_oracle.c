@@ -309,9 +309,7 @@ int sgrace_oracle_qlayer(const sgo_qlayer_t *d)
 
     float *Wh = d->Wh ? d->Wh : (float *)malloc(sizeof(float) * (size_t)N * P);
     if (!Wh) return -2;
-    const float inv_fs = q ? (float)(1.0 / (double)d->f_s) : 0.f;
-    const float inv_ws = q ? (float)(1.0 / (double)d->w_s) : 0.f;
-    const float inv_as = q ? (float)(1.0 / (double)d->a_s) : 0.f;
+    const float inv_fs = d->qscale_fea, inv_ws = d->qscale_w, inv_as = d->qscale_adj;
     int64_t maxabs = 0;
 
     if (q) {

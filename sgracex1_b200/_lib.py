@@ -1,0 +1,199 @@
+"""ctypes binding of libsgrace_b200.so (include/sgrace_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsgrace_b200.so")
+
+# enums of include/sgrace_b200.h
+MODE_F32_FAST, MODE_F32_CSIM, MODE_F16_CSIM, MODE_FIX16_CSIM, MODE_FULL = 0, 1, 2, 3, 4
+(OPT_MODE, OPT_SPMM_BLOCK, OPT_LAT_FEA, OPT_LAT_ADJ, OPT_FEA_THREADS, OPT_ADJ_THREADS,
+ OPT_USE_SBLOCKS, OPT_INDEX_FORMAT, OPT_QBITS, OPT_STAGING, OPT_LONG_ROW, OPT_LEAKY_ALPHA_BITS,
+ OPT_VALIDATE, OPT_DENSE_TC) = range(1, 15)
+REG_CTRL, REG_MAX_FEA = 0x00, 0x70
+
+EXPORTS = (
+    "sgrace_create", "sgrace_destroy", "sgrace_last_error", "sgrace_version", "sgrace_alloc",
+    "sgrace_free", "sgrace_sync_to_device", "sgrace_sync_from_device", "sgrace_write_reg",
+    "sgrace_read_reg", "sgrace_write_reg64", "sgrace_reg_offset", "sgrace_set_option",
+    "sgrace_get_option", "sgrace_set_stream", "sgrace_start", "sgrace_done", "sgrace_wait",
+    "sgrace_stage_times", "sgrace_layer_run", "sgrace_fea_run", "sgrace_adj_run",
+    "sgrace_launch_count",
+)
+
+
+class LayerDesc(C.Structure):
+    """sgrace_layer_desc"""
+    _fields_ = [
+        ("gemm_mode", C.c_int32), ("relu", C.c_int32), ("gat_mode", C.c_int32),
+        ("N_adj", C.c_int32), ("M_adj", C.c_int32), ("M_fea", C.c_int32), ("P_w", C.c_int32),
+        ("nnz_fea", C.c_int32), ("nnz_adj", C.c_int32),
+        ("scale_fea", C.c_int32), ("internal_quantization", C.c_int32),
+        ("qscale_fea", C.c_float), ("qscale_w", C.c_float), ("qscale_adj", C.c_float),
+        ("deq_factor", C.c_float),
+        ("rowPtr_fea", C.c_void_p), ("columnIndex_fea", C.c_void_p), ("values_fea", C.c_void_p),
+        ("rowPtr_adj", C.c_void_p), ("columnIndex_adj", C.c_void_p), ("values_adj", C.c_void_p),
+        ("B", C.c_void_p), ("attention", C.c_void_p), ("D", C.c_void_p),
+        ("E", C.c_void_p), ("S", C.c_void_p), ("XW", C.c_void_p),
+    ]
+
+
+class SgraceError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libsgrace_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load libsgrace_b200.so; fail loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the sm_100a CUDA library is not built. Run "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (or sgracex1_b200/csrc/build.sh). "
+            "There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    H = C.c_void_p
+    lib.sgrace_create.argtypes = [C.c_int, C.POINTER(H)]
+    lib.sgrace_destroy.argtypes = [H]
+    lib.sgrace_last_error.argtypes = [H]
+    lib.sgrace_last_error.restype = C.c_char_p
+    lib.sgrace_version.restype = C.c_char_p
+    lib.sgrace_alloc.argtypes = [H, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    lib.sgrace_free.argtypes = [H, C.c_uint64]
+    lib.sgrace_sync_to_device.argtypes = [H, C.c_uint64, C.c_size_t]
+    lib.sgrace_sync_from_device.argtypes = [H, C.c_uint64, C.c_size_t]
+    lib.sgrace_write_reg.argtypes = [H, C.c_uint32, C.c_uint32]
+    lib.sgrace_read_reg.argtypes = [H, C.c_uint32, C.POINTER(C.c_uint32)]
+    lib.sgrace_write_reg64.argtypes = [H, C.c_uint32, C.c_uint64]
+    lib.sgrace_reg_offset.argtypes = [C.c_char_p, C.POINTER(C.c_uint32)]
+    lib.sgrace_set_option.argtypes = [H, C.c_int, C.c_int64]
+    lib.sgrace_get_option.argtypes = [H, C.c_int, C.POINTER(C.c_int64)]
+    lib.sgrace_set_stream.argtypes = [H, C.c_void_p]
+    lib.sgrace_start.argtypes = [H]
+    lib.sgrace_done.argtypes = [H, C.POINTER(C.c_int)]
+    lib.sgrace_wait.argtypes = [H]
+    lib.sgrace_stage_times.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.sgrace_layer_run.argtypes = [H, C.POINTER(LayerDesc)]
+    lib.sgrace_fea_run.argtypes = [H, C.POINTER(LayerDesc), C.c_void_p]
+    lib.sgrace_adj_run.argtypes = [H, C.POINTER(LayerDesc), C.c_void_p, C.c_int32]
+    lib.sgrace_launch_count.argtypes = [H, C.POINTER(C.c_uint64)]
+    for name in EXPORTS:
+        if name not in ("sgrace_last_error", "sgrace_version"):
+            getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def reg_offset(name: str):
+    """AXI-Lite offset of a register name, or None when the map does not know it."""
+    off = C.c_uint32()
+    rc = load().sgrace_reg_offset(name.encode(), C.byref(off))
+    return int(off.value) if rc == 0 else None
+
+
+class Handle:
+    """One accelerator instance (one CUDA stream), the stand-in for `ol.mmult_top_0`."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        self.h = C.c_void_p()
+        rc = self.lib.sgrace_create(int(device), C.byref(self.h))
+        if rc != 0:
+            raise SgraceError(rc, f"sgrace_create(device={device}) failed -- is a CUDA device visible?")
+        self.device = int(device)
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SgraceError(rc, self.lib.sgrace_last_error(self.h).decode(errors="replace"))
+
+    def close(self):
+        if self.h:
+            self.lib.sgrace_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # options ---------------------------------------------------------------
+    def set_option(self, key, value):
+        self._ck(self.lib.sgrace_set_option(self.h, int(key), int(value)))
+
+    def get_option(self, key):
+        v = C.c_int64()
+        self._ck(self.lib.sgrace_get_option(self.h, int(key), C.byref(v)))
+        return int(v.value)
+
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self.lib.sgrace_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    # buffers ---------------------------------------------------------------
+    def alloc(self, nbytes):
+        host, dev = C.c_void_p(), C.c_uint64()
+        self._ck(self.lib.sgrace_alloc(self.h, int(nbytes), C.byref(host), C.byref(dev)))
+        return int(host.value), int(dev.value)
+
+    def free(self, dev_addr):
+        self._ck(self.lib.sgrace_free(self.h, int(dev_addr)))
+
+    def sync_to_device(self, dev_addr, nbytes):
+        self._ck(self.lib.sgrace_sync_to_device(self.h, int(dev_addr), int(nbytes)))
+
+    def sync_from_device(self, dev_addr, nbytes):
+        self._ck(self.lib.sgrace_sync_from_device(self.h, int(dev_addr), int(nbytes)))
+
+    # registers -------------------------------------------------------------
+    def write_reg(self, off, value):
+        self._ck(self.lib.sgrace_write_reg(self.h, int(off), int(value) & 0xFFFFFFFF))
+
+    def write_reg64(self, off, value):
+        self._ck(self.lib.sgrace_write_reg64(self.h, int(off), int(value) & 0xFFFFFFFFFFFFFFFF))
+
+    def read_reg(self, off):
+        v = C.c_uint32()
+        self._ck(self.lib.sgrace_read_reg(self.h, int(off), C.byref(v)))
+        return int(v.value)
+
+    # run -------------------------------------------------------------------
+    def start(self):
+        self._ck(self.lib.sgrace_start(self.h))
+
+    def done(self):
+        d = C.c_int()
+        self._ck(self.lib.sgrace_done(self.h, C.byref(d)))
+        return bool(d.value)
+
+    def wait(self):
+        self._ck(self.lib.sgrace_wait(self.h))
+
+    def stage_times(self):
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        self._ck(self.lib.sgrace_stage_times(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return float(a.value), float(b.value), float(c.value)
+
+    def layer_run(self, desc: LayerDesc):
+        self._ck(self.lib.sgrace_layer_run(self.h, C.byref(desc)))
+
+    def fea_run(self, desc: LayerDesc, xw_out_ptr):
+        self._ck(self.lib.sgrace_fea_run(self.h, C.byref(desc), C.c_void_p(xw_out_ptr)))
+
+    def adj_run(self, desc: LayerDesc, xw_in_ptr, xw_rows):
+        self._ck(self.lib.sgrace_adj_run(self.h, C.byref(desc), C.c_void_p(xw_in_ptr), int(xw_rows)))
+
+    def launch_count(self):
+        v = C.c_uint64()
+        self._ck(self.lib.sgrace_launch_count(self.h, C.byref(v)))
+        return int(v.value)

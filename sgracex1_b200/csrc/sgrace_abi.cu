@@ -1,0 +1,953 @@
+// sgrace_abi.cu -- C ABI of libsgrace_b200.so (see include/sgrace_b200.h).
+//
+// Host-side replacement for the bottom half of the reference driver: the AXI-Lite register
+// file + DMA buffers + AP_START/AP_DONE of `mmult_top` (kernelMatrixmult_all.cpp:3762-3967,
+// demo/sgrace_lib/sgrace.py:321-559) become a handle that owns a CUDA stream, a register
+// array, pinned-host/device buffer pairs and grow-only scratch, and dispatches the sm_100a
+// kernels of sgrace_kernels.cuh.  There is no CPU compute path in this library.
+#include "../../include/sgrace_b200.h"
+#include "sgrace_kernels.cuh"
+#include "sgrace_gemm_tc.cuh"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace sgrace;
+
+namespace {
+
+struct Buffer {
+    void* host = nullptr;
+    void* dev = nullptr;
+    size_t bytes = 0;
+};
+
+struct Scratch {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct sgrace_handle {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    uint32_t regs[SGRACE_REG_FILE_BYTES / 4];
+    std::map<uint64_t, Buffer> buffers;   // keyed by device base address
+    // options
+    int mode = SGRACE_MODE_F32_FAST;
+    int spmm_block = 1, lat_fea = 0, lat_adj = 0, fea_threads = 1, adj_threads = 1, use_sblocks = 0;
+    int index_format = 0, qbits = 8, staging = 1, long_row = 512, validate = 0, dense_tc = 1;
+    float leaky_alpha = 0.2f;
+    // scratch (grow-only)
+    Scratch wrm, xw, wq, s1, s2, rp_fea, rp_adj, lists, counters;
+    int* max_fea_dev = nullptr;
+    // state
+    bool running = false;
+    int last_status = 0;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // kernels start, fea done, adj done, all done, start (incl. staging)
+    bool ev_valid = false;
+    uint64_t launches = 0;
+    // pending device->host copies recorded at start (staging)
+    char err[512];
+};
+
+namespace {
+
+int fail(sgrace_handle* h, int code, const char* fmt, ...) {
+    if (h) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(h->err, sizeof(h->err), fmt, ap);
+        va_end(ap);
+        h->last_status = code;
+    }
+    return code;
+}
+
+#define CU(call)                                                                           \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess)                                                             \
+            return fail(h, SGRACE_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                               \
+    } while (0)
+
+int ensure(sgrace_handle* h, Scratch& s, size_t bytes) {
+    if (bytes <= s.bytes) return 0;
+    if (s.p) { CU(cudaStreamSynchronize(h->stream)); CU(cudaFree(s.p)); s.p = nullptr; s.bytes = 0; }
+    size_t want = bytes + bytes / 4 + 256;
+    CU(cudaMalloc(&s.p, want));
+    s.bytes = want;
+    return 0;
+}
+
+size_t elt_bytes(int mode) {
+    return (mode == SGRACE_MODE_F16_CSIM || mode == SGRACE_MODE_FIX16_CSIM) ? 2 : 4;
+}
+
+int default_lat(int mode) {   // matrix_mult.h:117-118,137-138,149-150
+    switch (mode) {
+        case SGRACE_MODE_F32_CSIM: return 6;
+        case SGRACE_MODE_F16_CSIM: return 4;
+        default: return 1;
+    }
+}
+
+inline int grid_for(long long work_items, int block, int num_sms, int max_waves = 32) {
+    long long g = (work_items + block - 1) / block;
+    long long cap = (long long)num_sms * max_waves;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// ------------------------------------------------------------------------------------
+// fast float32 SpMM dispatch
+// ------------------------------------------------------------------------------------
+template <int LPR, int NV>
+int launch_spmm_vec(sgrace_handle* h, const int* rp, const int* ci, const float* va, const float* Bm,
+                    float* out, int nrows, int P, int relu) {
+    const int P4 = P / 4;
+    constexpr int RPW = 32 / LPR;
+    // room for the long-row list: nrows ints + counter
+    if (int rc = ensure(h, h->lists, sizeof(int) * (size_t)(nrows > 0 ? nrows : 1))) return rc;
+    if (int rc = ensure(h, h->counters, 64)) return rc;
+    int* long_rows = (int*)h->lists.p;
+    int* long_count = (int*)h->counters.p;
+    CU(cudaMemsetAsync(long_count, 0, sizeof(int), h->stream));
+    const int block = 256;
+    long long warps = ((long long)nrows + RPW - 1) / RPW;
+    // persistent-ish grid: a multiple of the SM count, 8 CTAs of 256 threads per SM resident
+    int grid = grid_for(warps * 32, block, h->num_sms, 8);
+    if (grid > h->num_sms) grid = (grid / h->num_sms) * h->num_sms;
+    spmm_csr_f32_kernel<LPR, NV><<<grid, block, 0, h->stream>>>(
+        rp, ci, va, (const float4*)Bm, (float4*)out, nrows, P4, relu, h->long_row, long_rows, long_count);
+    h->launches++;
+    CU(cudaGetLastError());
+    // long rows (power-law graphs): CTA per row, deterministic in-CTA reduction
+    constexpr int NVL = (LPR * NV + 31) / 32 > 0 ? (LPR * NV + 31) / 32 : 1;
+    size_t smem = sizeof(float4) * 8 * (size_t)P4;
+    if (smem > 48 * 1024)
+        CU(cudaFuncSetAttribute(spmm_long_rows_f32_kernel<NVL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
+    spmm_long_rows_f32_kernel<NVL><<<h->num_sms * 2, 256, smem, h->stream>>>(
+        rp, ci, va, (const float4*)Bm, (float4*)out, P4, relu, long_rows, long_count);
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+template <int NC>
+int launch_spmm_scalar(sgrace_handle* h, const int* rp, const int* ci, const float* va, const float* Bm,
+                       float* out, int nrows, int P, int relu) {
+    int grid = grid_for((long long)nrows * 32, 256, h->num_sms, 8);
+    spmm_csr_f32_scalar_kernel<NC><<<grid, 256, 0, h->stream>>>(rp, ci, va, Bm, out, nrows, P, relu);
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int spmm_f32(sgrace_handle* h, const int* rp, const int* ci, const float* va, const float* Bm, float* out,
+             int nrows, int P, int relu) {
+    if (nrows <= 0 || P <= 0) return 0;
+    const bool aligned = (P % 4 == 0) && (((uintptr_t)Bm & 15) == 0) && (((uintptr_t)out & 15) == 0);
+    if (aligned) {
+        const int P4 = P / 4;
+        if (P4 == 1) return launch_spmm_vec<1, 1>(h, rp, ci, va, Bm, out, nrows, P, relu);
+        if (P4 == 2) return launch_spmm_vec<2, 1>(h, rp, ci, va, Bm, out, nrows, P, relu);
+        if (P4 <= 4) return launch_spmm_vec<4, 1>(h, rp, ci, va, Bm, out, nrows, P, relu);
+        if (P4 <= 8) return launch_spmm_vec<8, 1>(h, rp, ci, va, Bm, out, nrows, P, relu);
+        if (P4 <= 16) return launch_spmm_vec<16, 1>(h, rp, ci, va, Bm, out, nrows, P, relu);
+        if (P4 <= 32) return launch_spmm_vec<32, 1>(h, rp, ci, va, Bm, out, nrows, P, relu);
+        if (P4 <= 64) return launch_spmm_vec<32, 2>(h, rp, ci, va, Bm, out, nrows, P, relu);
+        if (P4 <= 128) return launch_spmm_vec<32, 4>(h, rp, ci, va, Bm, out, nrows, P, relu);
+        if (P4 <= 256) return launch_spmm_vec<32, 8>(h, rp, ci, va, Bm, out, nrows, P, relu);
+        return fail(h, SGRACE_EUNSUPPORTED, "P_w=%d > 1024 not supported", P);
+    }
+    if (P <= 32) return launch_spmm_scalar<1>(h, rp, ci, va, Bm, out, nrows, P, relu);
+    if (P <= 64) return launch_spmm_scalar<2>(h, rp, ci, va, Bm, out, nrows, P, relu);
+    if (P <= 128) return launch_spmm_scalar<4>(h, rp, ci, va, Bm, out, nrows, P, relu);
+    if (P <= 256) return launch_spmm_scalar<8>(h, rp, ci, va, Bm, out, nrows, P, relu);
+    if (P <= 1024) return launch_spmm_scalar<32>(h, rp, ci, va, Bm, out, nrows, P, relu);
+    return fail(h, SGRACE_EUNSUPPORTED, "P_w=%d > 1024 not supported", P);
+}
+
+// ------------------------------------------------------------------------------------
+// bit-exact C-simulation-order stage dispatch
+// ------------------------------------------------------------------------------------
+template <typename Ops>
+int stage_exact(sgrace_handle* h, int lat, const int* rp, const int* ci, const void* va, const void* Bm,
+                void* out, int nrows, int P, int hw_threads, int sblock, int dense_M, int relu) {
+    typedef typename Ops::T T;
+    if (nrows <= 0 || P <= 0) return 0;
+    long long items = (long long)nrows * P;
+    int block = 256;
+    long long g = (items + block - 1) / block;
+    if (g > 0x7fffffffLL) return fail(h, SGRACE_EUNSUPPORTED, "problem too large for exact kernel");
+    int grid = (int)g;
+#define LAUNCH_LAT(L)                                                                              \
+    stage_exact_kernel<Ops, L><<<grid, block, 0, h->stream>>>(rp, ci, (const T*)va, (const T*)Bm, \
+                                                              (T*)out, nrows, P, hw_threads, sblock, dense_M, relu)
+    switch (lat) {
+        case 1: LAUNCH_LAT(1); break;
+        case 2: LAUNCH_LAT(2); break;
+        case 3: LAUNCH_LAT(3); break;
+        case 4: LAUNCH_LAT(4); break;
+        case 5: LAUNCH_LAT(5); break;
+        case 6: LAUNCH_LAT(6); break;
+        case 7: LAUNCH_LAT(7); break;
+        case 8: LAUNCH_LAT(8); break;
+        default: return fail(h, SGRACE_EUNSUPPORTED, "FADD latency %d not in 1..8", lat);
+    }
+#undef LAUNCH_LAT
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int stage_exact_any(sgrace_handle* h, int mode, int lat, const int* rp, const int* ci, const void* va,
+                    const void* Bm, void* out, int nrows, int P, int hw_threads, int sblock, int dense_M,
+                    int relu) {
+    switch (mode) {
+        case SGRACE_MODE_F32_CSIM:
+            return stage_exact<OpsF32>(h, lat, rp, ci, va, Bm, out, nrows, P, hw_threads, sblock, dense_M, relu);
+        case SGRACE_MODE_F16_CSIM:
+            return stage_exact<OpsF16>(h, lat, rp, ci, va, Bm, out, nrows, P, hw_threads, sblock, dense_M, relu);
+        case SGRACE_MODE_FIX16_CSIM:
+            return stage_exact<OpsFix16>(h, 1, rp, ci, va, Bm, out, nrows, P, hw_threads, sblock, dense_M, relu);
+    }
+    return fail(h, SGRACE_EINVAL, "bad exact mode %d", mode);
+}
+
+template <typename T>
+int transpose_b(sgrace_handle* h, const void* B, void* Wrm, int M, int P) {
+    dim3 grid((M + 31) / 32, (P + 31) / 32), block(32, 8);
+    transpose_b_kernel<T><<<grid, block, 0, h->stream>>>((const T*)B, (T*)Wrm, M, P);
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int make_rowptr(sgrace_handle* h, Scratch& s, const int* rows, int nnz, int n, const int** out) {
+    if (int rc = ensure(h, s, sizeof(int) * (size_t)(n + 1))) return rc;
+    int grid = (n + 1 + 255) / 256;
+    coo_rows_to_rowptr_kernel<<<grid, 256, 0, h->stream>>>(rows, nnz, n, (int*)s.p);
+    h->launches++;
+    CU(cudaGetLastError());
+    *out = (const int*)s.p;
+    return 0;
+}
+
+QConst make_qconst(const sgrace_handle* h, const sgrace_layer_desc* d) {
+    QConst q;
+    memset(&q, 0, sizeof(q));
+    q.inv_fs = d->qscale_fea; q.inv_ws = d->qscale_w; q.inv_as = d->qscale_adj;
+    q.f_z = q.w_z = q.a_z = 0;   // the driver never programs zero points (sgrace.py:334-365)
+    q.qbits = h->qbits;
+    q.den = h->qbits == 1 ? 2.0f : (float)(1 << (h->qbits > 0 ? h->qbits - 1 : 0));
+    q.wh_den = q.den * q.den;
+    q.wh_scale = (float)(1 << d->scale_fea);
+    const int iq = d->internal_quantization;
+    q.a_hi = (float)((ldexp(1.0, iq) - 1.0) / ldexp(1.0, iq));
+    q.round_T = (float)pow(10.0, (double)(iq - 1));
+    q.deq_o = d->deq_factor;
+    q.alpha = h->leaky_alpha;
+    return q;
+}
+
+// ------------------------------------------------------------------------------------
+// the two stages
+// ------------------------------------------------------------------------------------
+int resolve_rowptrs(sgrace_handle* h, const sgrace_layer_desc* d, const int** rp_fea, const int** rp_adj,
+                    bool need_fea, bool need_adj) {
+    *rp_fea = d->rowPtr_fea;
+    *rp_adj = d->rowPtr_adj;
+    if (h->index_format == 1) {
+        if (need_fea && d->gemm_mode == 0)
+            if (int rc = make_rowptr(h, h->rp_fea, d->rowPtr_fea, d->nnz_fea, d->N_adj, rp_fea)) return rc;
+        if (need_adj)
+            if (int rc = make_rowptr(h, h->rp_adj, d->rowPtr_adj, d->nnz_adj, d->N_adj, rp_adj)) return rc;
+    }
+    return 0;
+}
+
+int run_fea(sgrace_handle* h, const sgrace_layer_desc* d, const int* rp_fea, void* XW) {
+    const int N = d->N_adj, M = d->M_fea, P = d->P_w;
+    if (N <= 0 || P <= 0) return 0;
+    if (!d->B || !d->values_fea) return fail(h, SGRACE_EINVAL, "B / values_fea pointer not set");
+    if (d->gemm_mode == 0 && (!rp_fea || !d->columnIndex_fea))
+        return fail(h, SGRACE_EINVAL, "rowPtr_fea / columnIndex_fea pointer not set");
+    const size_t esz = elt_bytes(h->mode);
+    switch (h->mode) {
+        case SGRACE_MODE_F32_FAST: {
+            if (int rc = ensure(h, h->wrm, esz * (size_t)M * P)) return rc;
+            if (int rc = transpose_b<float>(h, d->B, h->wrm.p, M, P)) return rc;
+            if (d->gemm_mode == 0)
+                return spmm_f32(h, rp_fea, d->columnIndex_fea, (const float*)d->values_fea,
+                                (const float*)h->wrm.p, (float*)XW, N, P, 0);
+            if (h->dense_tc && fea_dense_tc_supported(N, M, P)) {
+                int rc = fea_dense_tc_launch((const float*)d->values_fea, (const float*)d->B, (float*)XW, N, M, P,
+                                             h->num_sms, h->stream);
+                if (rc == 0) { h->launches++; return 0; }
+                if (rc != -100) return fail(h, SGRACE_ECUDA, "tcgen05 dense FEA launch failed (%d)", rc);
+            }
+            dim3 grid((N + 63) / 64, (P + 63) / 64);
+            fea_dense_f32_kernel<<<grid, 256, 0, h->stream>>>((const float*)d->values_fea,
+                                                               (const float*)h->wrm.p, (float*)XW, N, M, P);
+            h->launches++;
+            CU(cudaGetLastError());
+            return 0;
+        }
+        case SGRACE_MODE_F32_CSIM:
+        case SGRACE_MODE_F16_CSIM:
+        case SGRACE_MODE_FIX16_CSIM: {
+            if (int rc = ensure(h, h->wrm, esz * (size_t)M * P)) return rc;
+            if (esz == 4) { if (int rc = transpose_b<float>(h, d->B, h->wrm.p, M, P)) return rc; }
+            else          { if (int rc = transpose_b<unsigned short>(h, d->B, h->wrm.p, M, P)) return rc; }
+            const int lat = h->lat_fea > 0 ? h->lat_fea : default_lat(h->mode);
+            return stage_exact_any(h, h->mode, lat, rp_fea, d->columnIndex_fea, d->values_fea, h->wrm.p, XW, N, P,
+                                   h->fea_threads, h->spmm_block, d->gemm_mode ? M : 0, 0);
+        }
+        case SGRACE_MODE_FULL: {
+            if (h->qbits == 0) {   // fake_quantization == 0: float32, multiply-then-add in row order
+                if (int rc = ensure(h, h->wrm, 4 * (size_t)M * P)) return rc;
+                if (int rc = transpose_b<float>(h, d->B, h->wrm.p, M, P)) return rc;
+                return stage_exact<OpsF32>(h, 1, rp_fea, d->columnIndex_fea, d->values_fea, h->wrm.p, XW, N, P, 1, 1,
+                                           d->gemm_mode ? M : 0, 0);
+            }
+            const QConst qc = make_qconst(h, d);
+            const int Pp = (P + 3) & ~3;
+            if (int rc = ensure(h, h->wq, (size_t)M * Pp)) return rc;
+            quantize_w_kernel<<<(M * Pp + 255) / 256, 256, 0, h->stream>>>((const float*)d->B, (signed char*)h->wq.p,
+                                                                           M, P, Pp, qc);
+            h->launches++;
+            CU(cudaGetLastError());
+            if (!h->max_fea_dev) CU(cudaMalloc(&h->max_fea_dev, sizeof(int)));
+            CU(cudaMemsetAsync(h->max_fea_dev, 0, sizeof(int), h->stream));
+            long long items = (long long)N * (Pp / 4);
+            int grid = (int)((items + 255) / 256);
+            if (d->gemm_mode == 0)
+                fea_q_csr_kernel<<<grid, 256, 0, h->stream>>>(rp_fea, d->columnIndex_fea, (const float*)d->values_fea,
+                                                              (const signed char*)h->wq.p, (float*)XW, N, P, Pp, qc,
+                                                              h->max_fea_dev);
+            else
+                fea_q_dense_kernel<<<grid, 256, 0, h->stream>>>((const float*)d->values_fea,
+                                                                (const signed char*)h->wq.p, (float*)XW, N, M, P, Pp,
+                                                                qc, h->max_fea_dev);
+            h->launches++;
+            CU(cudaGetLastError());
+            return 0;
+        }
+    }
+    return fail(h, SGRACE_EINVAL, "bad mode %d", h->mode);
+}
+
+int run_adj(sgrace_handle* h, const sgrace_layer_desc* d, const int* rp_adj, const void* XW, int xw_rows) {
+    const int N = d->N_adj, P = d->P_w;
+    (void)xw_rows;
+    if (N <= 0 || P <= 0) return 0;
+    if (!rp_adj || !d->columnIndex_adj || !d->values_adj || !d->D)
+        return fail(h, SGRACE_EINVAL, "adjacency / D pointer not set");
+    // USE_SBLOCKS == 1 drops the ReLU in the reference's write stage (kernelMatrixmult_all.cpp:748-786)
+    const int relu = (h->use_sblocks && h->mode != SGRACE_MODE_FULL && h->mode != SGRACE_MODE_F32_FAST)
+                         ? 0 : (d->relu != 0);
+    switch (h->mode) {
+        case SGRACE_MODE_F32_FAST:
+            return spmm_f32(h, rp_adj, d->columnIndex_adj, (const float*)d->values_adj, (const float*)XW,
+                            (float*)d->D, N, P, relu);
+        case SGRACE_MODE_F32_CSIM:
+        case SGRACE_MODE_F16_CSIM:
+        case SGRACE_MODE_FIX16_CSIM: {
+            const int lat = h->lat_adj > 0 ? h->lat_adj : default_lat(h->mode);
+            return stage_exact_any(h, h->mode, lat, rp_adj, d->columnIndex_adj, d->values_adj, XW, d->D, N, P,
+                                   h->adj_threads, h->spmm_block, 0, relu);
+        }
+        case SGRACE_MODE_FULL: {
+            const QConst qc = make_qconst(h, d);
+            const int quant = h->qbits > 0;
+            if (!d->gat_mode) {
+                long long items = (long long)N * P;
+                adj_q_gcn_kernel<<<(int)((items + 255) / 256), 256, 0, h->stream>>>(
+                    rp_adj, d->columnIndex_adj, (const float*)d->values_adj, (const float*)XW, (float*)d->D, N, P,
+                    relu, quant, qc);
+                h->launches++;
+                CU(cudaGetLastError());
+                return 0;
+            }
+            if (!d->attention) return fail(h, SGRACE_EINVAL, "gat_mode set but ate_m (attention) pointer missing");
+            if (int rc = ensure(h, h->s1, sizeof(float) * (size_t)xw_rows)) return rc;
+            if (int rc = ensure(h, h->s2, sizeof(float) * (size_t)xw_rows)) return rc;
+            if (int rc = ensure(h, h->lists, sizeof(int) * (size_t)N)) return rc;
+            if (int rc = ensure(h, h->counters, 64)) return rc;
+            int* empty_count = (int*)h->counters.p + 1;
+            CU(cudaMemsetAsync(empty_count, 0, sizeof(int), h->stream));
+            gat_scores_kernel<<<(xw_rows + 255) / 256, 256, 0, h->stream>>>((const float*)XW, d->attention,
+                                                                            (float*)h->s1.p, (float*)h->s2.p, xw_rows,
+                                                                            P, quant, qc);
+            h->launches++;
+            CU(cudaGetLastError());
+            int grid = grid_for((long long)N * 32, 256, h->num_sms, 8);
+            gat_aggregate_kernel<<<grid, 256, 0, h->stream>>>(rp_adj, d->columnIndex_adj, (const float*)d->values_adj,
+                                                              (const float*)XW, (const float*)h->s1.p,
+                                                              (const float*)h->s2.p, (float*)d->D, d->E, d->S, N, P,
+                                                              relu, quant, qc, (int*)h->lists.p, empty_count);
+            h->launches++;
+            CU(cudaGetLastError());
+            gat_empty_rows_kernel<<<(P + 127) / 128, 128, 0, h->stream>>>((const float*)XW, (float*)d->D, xw_rows, P,
+                                                                          relu, quant, qc, (const int*)h->lists.p,
+                                                                          empty_count);
+            h->launches++;
+            CU(cudaGetLastError());
+            return 0;
+        }
+    }
+    return fail(h, SGRACE_EINVAL, "bad mode %d", h->mode);
+}
+
+int check_desc(sgrace_handle* h, const sgrace_layer_desc* d) {
+    if (!d) return fail(h, SGRACE_EINVAL, "null descriptor");
+    if (d->N_adj < 0 || d->M_fea < 0 || d->P_w < 0) return fail(h, SGRACE_EINVAL, "negative dimension");
+    if (d->gemm_mode == 2)
+        return fail(h, SGRACE_EUNSUPPORTED,
+                    "gemm_mode=2 (hardware backward, sgrace.py:717) is not implemented; use the saved-tensor backward");
+    if (d->gemm_mode != 0 && d->gemm_mode != 1) return fail(h, SGRACE_EINVAL, "gemm_mode=%d", d->gemm_mode);
+    if (h->index_format == 1 && ((d->gemm_mode == 0 && d->nnz_fea < 0) || d->nnz_adj < 0))
+        return fail(h, SGRACE_EINVAL, "COO index format needs nnz_fea1 / nnz_adj1");
+    if (h->mode == SGRACE_MODE_FULL && h->qbits > 0) {
+        if (d->internal_quantization < 1 || d->internal_quantization > 30 || d->scale_fea < 0 || d->scale_fea > 30)
+            return fail(h, SGRACE_EINVAL, "scale_fea / quantized_multiplier registers out of range");
+        if (!(d->qscale_fea > 0.f) || !(d->qscale_w > 0.f) || !(d->qscale_adj > 0.f))
+            return fail(h, SGRACE_EINVAL, "quantization_scale_* registers not programmed");
+    }
+    return 0;
+}
+
+int layer_run_impl(sgrace_handle* h, const sgrace_layer_desc* d, bool timed) {
+    if (int rc = check_desc(h, d)) return rc;
+    const size_t esz = elt_bytes(h->mode);
+    void* XW = d->XW;
+    if (!XW) {
+        if (int rc = ensure(h, h->xw, esz * (size_t)d->N_adj * (size_t)d->P_w + 16)) return rc;
+        XW = h->xw.p;
+    }
+    const int *rp_fea, *rp_adj;
+    if (timed) CU(cudaEventRecord(h->ev[0], h->stream));
+    if (int rc = resolve_rowptrs(h, d, &rp_fea, &rp_adj, true, true)) return rc;
+    if (int rc = run_fea(h, d, rp_fea, XW)) return rc;
+    if (timed) CU(cudaEventRecord(h->ev[1], h->stream));
+    if (int rc = run_adj(h, d, rp_adj, XW, d->N_adj)) return rc;
+    if (timed) CU(cudaEventRecord(h->ev[2], h->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// register file helpers
+// ------------------------------------------------------------------------------------
+struct RegName { const char* name; uint32_t off; };
+const RegName kRegNames[] = {
+    {"CTRL", 0x00}, {"GIER", 0x04}, {"IP_IER", 0x08}, {"IP_ISR", 0x0c},
+    {"load_weights", 0x10}, {"beta_qu", 0x18}, {"f_align", 0x20},
+    {"quantization_scale_adj", 0x28}, {"quantization_scale_fea", 0x30}, {"quantization_scale_w", 0x38},
+    {"deq_factor", 0x40}, {"stream_mode", 0x48}, {"gat_mode", 0x50}, {"gemm_mode", 0x58}, {"relu", 0x60},
+    {"scale_fea", 0x68}, {"max_fea", 0x70}, {"max_fea_ctrl", 0x74}, {"layer_count", 0x80},
+    {"quantized_multiplier", 0x88}, {"shift_offset_1", 0x90}, {"shift_offset_2", 0x94},
+    {"bias_offset_1", 0x9c}, {"bias_offset_2", 0xa0}, {"bias_count", 0xa8},
+    {"profiling_offset_1", 0xb0}, {"profiling_offset_2", 0xb4},
+    {"zero_point_lhs", 0xbc}, {"zero_point_rhs", 0xc4}, {"zero_point_dst", 0xcc},
+    {"clamp_max", 0xd4}, {"clamp_min", 0xdc},
+    {"N_adj", 0xe4}, {"M_adj", 0xec}, {"M_fea", 0xf4}, {"P_w", 0xfc},
+    {"B_offset_1", 0x104}, {"B_offset_2", 0x108},
+    {"D1_offset_1", 0x110}, {"D1_offset_2", 0x114}, {"D2_offset_1", 0x11c}, {"D2_offset_2", 0x120},
+    {"D3_offset_1", 0x128}, {"D3_offset_2", 0x12c}, {"D4_offset_1", 0x134}, {"D4_offset_2", 0x138},
+    {"E1_offset_1", 0x140}, {"E1_offset_2", 0x144}, {"S1_offset_1", 0x14c}, {"S1_offset_2", 0x150},
+    {"ate_m_offset_1", 0x158}, {"ate_m_offset_2", 0x15c}, {"array_c_adjust", 0x164},
+    {"nnz_fea1", 0x16c}, {"nnz_fea2", 0x174}, {"nnz_fea3", 0x17c}, {"nnz_fea4", 0x184},
+    {"rowPtr_fea1_offset_1", 0x18c}, {"rowPtr_fea1_offset_2", 0x190},
+    {"rowPtr_fea2_offset_1", 0x198}, {"rowPtr_fea2_offset_2", 0x19c},
+    {"rowPtr_fea3_offset_1", 0x1a4}, {"rowPtr_fea3_offset_2", 0x1a8},
+    {"rowPtr_fea4_offset_1", 0x1b0}, {"rowPtr_fea4_offset_2", 0x1b4},
+    {"columnIndex_fea1_offset_1", 0x1bc}, {"columnIndex_fea1_offset_2", 0x1c0},
+    {"columnIndex_fea2_offset_1", 0x1c8}, {"columnIndex_fea2_offset_2", 0x1cc},
+    {"columnIndex_fea3_offset_1", 0x1d4}, {"columnIndex_fea3_offset_2", 0x1d8},
+    {"columnIndex_fea4_offset_1", 0x1e0}, {"columnIndex_fea4_offset_2", 0x1e4},
+    {"values_fea1_offset_1", 0x1ec}, {"values_fea1_offset_2", 0x1f0},
+    {"values_fea2_offset_1", 0x1f8}, {"values_fea2_offset_2", 0x1fc},
+    {"values_fea3_offset_1", 0x204}, {"values_fea3_offset_2", 0x208},
+    {"values_fea4_offset_1", 0x210}, {"values_fea4_offset_2", 0x214},
+    {"nnz_adj1", 0x21c}, {"nnz_adj2", 0x224}, {"nnz_adj3", 0x22c}, {"nnz_adj4", 0x234},
+    {"rowPtr_adj1_offset_1", 0x23c}, {"rowPtr_adj1_offset_2", 0x240},
+    {"rowPtr_adj2_offset_1", 0x248}, {"rowPtr_adj2_offset_2", 0x24c},
+    {"rowPtr_adj3_offset_1", 0x254}, {"rowPtr_adj3_offset_2", 0x258},
+    {"rowPtr_adj4_offset_1", 0x260}, {"rowPtr_adj4_offset_2", 0x264},
+    {"columnIndex_adj1_offset_1", 0x26c}, {"columnIndex_adj1_offset_2", 0x270},
+    {"columnIndex_adj2_offset_1", 0x278}, {"columnIndex_adj2_offset_2", 0x27c},
+    {"columnIndex_adj3_offset_1", 0x284}, {"columnIndex_adj3_offset_2", 0x288},
+    {"columnIndex_adj4_offset_1", 0x290}, {"columnIndex_adj4_offset_2", 0x294},
+    {"values_adj1_offset_1", 0x29c}, {"values_adj1_offset_2", 0x2a0},
+    {"values_adj2_offset_1", 0x2a8}, {"values_adj2_offset_2", 0x2ac},
+    {"values_adj3_offset_1", 0x2b4}, {"values_adj3_offset_2", 0x2b8},
+    {"values_adj4_offset_1", 0x2c0}, {"values_adj4_offset_2", 0x2c4},
+    {"quantized_multiplier_offset_1", 0x400}, {"quantized_multiplier_offset_2", 0x404},
+};
+
+inline uint64_t reg64(const sgrace_handle* h, uint32_t off) {
+    return (uint64_t)h->regs[off / 4] | ((uint64_t)h->regs[off / 4 + 1] << 32);
+}
+inline float regf(const sgrace_handle* h, uint32_t off) {
+    float f;
+    memcpy(&f, &h->regs[off / 4], 4);
+    return f;
+}
+
+// find the sgrace_alloc buffer containing device address a
+const Buffer* find_buffer(const sgrace_handle* h, uint64_t a, size_t* offset) {
+    if (h->buffers.empty() || a == 0) return nullptr;
+    auto it = h->buffers.upper_bound(a);
+    if (it == h->buffers.begin()) return nullptr;
+    --it;
+    if (a >= it->first && a < it->first + it->second.bytes) {
+        *offset = (size_t)(a - it->first);
+        return &it->second;
+    }
+    return nullptr;
+}
+
+int stage_in(sgrace_handle* h, uint64_t addr, size_t bytes) {
+    size_t off;
+    const Buffer* b = find_buffer(h, addr, &off);
+    if (!b || bytes == 0) return 0;
+    if (off + bytes > b->bytes)
+        return fail(h, SGRACE_EBOUNDS, "layer needs %zu bytes at buffer offset %zu but the allocation has %zu", bytes,
+                    off, b->bytes);
+    CU(cudaMemcpyAsync((char*)b->dev + off, (char*)b->host + off, bytes, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+int stage_out(sgrace_handle* h, uint64_t addr, size_t bytes) {
+    size_t off;
+    const Buffer* b = find_buffer(h, addr, &off);
+    if (!b || bytes == 0) return 0;
+    if (off + bytes > b->bytes)
+        return fail(h, SGRACE_EBOUNDS, "layer writes %zu bytes at buffer offset %zu but the allocation has %zu", bytes,
+                    off, b->bytes);
+    CU(cudaMemcpyAsync((char*)b->host + off, (char*)b->dev + off, bytes, cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+}
+const void* host_view(const sgrace_handle* h, uint64_t addr) {
+    size_t off;
+    const Buffer* b = find_buffer(h, addr, &off);
+    return b ? (const char*)b->host + off : nullptr;
+}
+
+int validate_csr_host(sgrace_handle* h, const int* rp, const int* ci, int n, int ncols, const char* what) {
+    for (int i = 0; i < n; i++)
+        if (rp[i + 1] < rp[i]) return fail(h, SGRACE_EBOUNDS, "%s: rowPtr not monotonic at row %d", what, i);
+    for (long long k = rp[0]; k < rp[n]; k++)
+        if (ci[k] < 0 || ci[k] >= ncols)
+            return fail(h, SGRACE_EBOUNDS, "%s: column index %d out of range [0,%d) at %lld", what, ci[k], ncols, k);
+    return 0;
+}
+
+}  // namespace
+
+// ====================================================================================
+// exported functions
+// ====================================================================================
+extern "C" {
+
+const char* sgrace_version(void) { return "sgrace_b200 0.1 (sm_100a)"; }
+
+int sgrace_create(int device, sgrace_handle** out) {
+    if (!out) return SGRACE_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) return SGRACE_ECUDA;
+    sgrace_handle* h = new (std::nothrow) sgrace_handle();
+    if (!h) return SGRACE_ENOMEM;
+    memset(h->regs, 0, sizeof(h->regs));
+    h->err[0] = 0;
+    h->device = device;
+    h->regs[0] = 0x4;   // AP_IDLE
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return SGRACE_ECUDA;
+    }
+    cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
+    for (int i = 0; i < 5; i++) cudaEventCreate(&h->ev[i]);
+    *out = h;
+    return SGRACE_OK;
+}
+
+int sgrace_destroy(sgrace_handle* h) {
+    if (!h) return SGRACE_EINVAL;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (auto& kv : h->buffers) {
+        cudaFree(kv.second.dev);
+        cudaFreeHost(kv.second.host);
+    }
+    Scratch* all[] = {&h->wrm, &h->xw, &h->wq, &h->s1, &h->s2, &h->rp_fea, &h->rp_adj, &h->lists, &h->counters};
+    for (Scratch* s : all) if (s->p) cudaFree(s->p);
+    if (h->max_fea_dev) cudaFree(h->max_fea_dev);
+    for (int i = 0; i < 5; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return SGRACE_OK;
+}
+
+const char* sgrace_last_error(sgrace_handle* h) { return h ? h->err : "null handle"; }
+
+int sgrace_alloc(sgrace_handle* h, size_t bytes, void** host_ptr, uint64_t* device_addr) {
+    if (!h || !host_ptr || !device_addr) return SGRACE_EINVAL;
+    CU(cudaSetDevice(h->device));
+    Buffer b;
+    b.bytes = bytes ? bytes : 1;
+    size_t padded = (b.bytes + 255) & ~(size_t)255;
+    CU(cudaMalloc(&b.dev, padded));
+    cudaError_t e = cudaHostAlloc(&b.host, padded, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaFree(b.dev);
+        return fail(h, SGRACE_ENOMEM, "cudaHostAlloc(%zu) failed: %s", padded, cudaGetErrorString(e));
+    }
+    memset(b.host, 0, padded);
+    CU(cudaMemsetAsync(b.dev, 0, padded, h->stream));
+    h->buffers[(uint64_t)(uintptr_t)b.dev] = b;
+    *host_ptr = b.host;
+    *device_addr = (uint64_t)(uintptr_t)b.dev;
+    return SGRACE_OK;
+}
+
+int sgrace_free(sgrace_handle* h, uint64_t device_addr) {
+    if (!h) return SGRACE_EINVAL;
+    auto it = h->buffers.find(device_addr);
+    if (it == h->buffers.end()) return fail(h, SGRACE_EINVAL, "sgrace_free: unknown buffer 0x%llx",
+                                            (unsigned long long)device_addr);
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(it->second.dev);
+    cudaFreeHost(it->second.host);
+    h->buffers.erase(it);
+    return SGRACE_OK;
+}
+
+int sgrace_sync_to_device(sgrace_handle* h, uint64_t device_addr, size_t bytes) {
+    if (!h) return SGRACE_EINVAL;
+    return stage_in(h, device_addr, bytes);
+}
+int sgrace_sync_from_device(sgrace_handle* h, uint64_t device_addr, size_t bytes) {
+    if (!h) return SGRACE_EINVAL;
+    if (int rc = stage_out(h, device_addr, bytes)) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    return SGRACE_OK;
+}
+
+int sgrace_reg_offset(const char* name, uint32_t* offset) {
+    if (!name || !offset) return SGRACE_EINVAL;
+    for (const RegName& r : kRegNames)
+        if (strcmp(r.name, name) == 0) { *offset = r.off; return SGRACE_OK; }
+    return SGRACE_EINVAL;
+}
+
+int sgrace_write_reg(sgrace_handle* h, uint32_t offset, uint32_t value) {
+    if (!h) return SGRACE_EINVAL;
+    if (offset % 4 || offset >= SGRACE_REG_FILE_BYTES) return fail(h, SGRACE_EINVAL, "bad register offset 0x%x", offset);
+    if (offset == SGRACE_REG_CTRL) {
+        if (value & 1u) return sgrace_start(h);   // CTRL.AP_START = 1
+        return SGRACE_OK;
+    }
+    if (offset == SGRACE_REG_MAX_FEA) return SGRACE_OK;   // read-only
+    h->regs[offset / 4] = value;
+    return SGRACE_OK;
+}
+
+int sgrace_write_reg64(sgrace_handle* h, uint32_t offset, uint64_t value) {
+    if (int rc = sgrace_write_reg(h, offset, (uint32_t)(value & 0xffffffffu))) return rc;
+    return sgrace_write_reg(h, offset + 4, (uint32_t)(value >> 32));
+}
+
+int sgrace_read_reg(sgrace_handle* h, uint32_t offset, uint32_t* value) {
+    if (!h || !value) return SGRACE_EINVAL;
+    if (offset % 4 || offset >= SGRACE_REG_FILE_BYTES) return fail(h, SGRACE_EINVAL, "bad register offset 0x%x", offset);
+    if (offset == SGRACE_REG_CTRL) {
+        int done = 0;
+        sgrace_done(h, &done);
+        // AP_DONE (bit1) and AP_READY (bit3) when finished, AP_IDLE (bit2) when nothing runs
+        *value = done ? 0xEu : 0x0u;
+        return SGRACE_OK;
+    }
+    *value = h->regs[offset / 4];
+    return SGRACE_OK;
+}
+
+int sgrace_set_option(sgrace_handle* h, int key, int64_t v) {
+    if (!h) return SGRACE_EINVAL;
+    switch (key) {
+        case SGRACE_OPT_MODE:
+            if (v < 0 || v > SGRACE_MODE_FULL) return fail(h, SGRACE_EINVAL, "bad mode %lld", (long long)v);
+            h->mode = (int)v; break;
+        case SGRACE_OPT_SPMM_BLOCK: if (v < 1) return fail(h, SGRACE_EINVAL, "spmm_block < 1"); h->spmm_block = (int)v; break;
+        case SGRACE_OPT_LAT_FEA: if (v < 0 || v > 8) return fail(h, SGRACE_EINVAL, "lat_fea not in 0..8"); h->lat_fea = (int)v; break;
+        case SGRACE_OPT_LAT_ADJ: if (v < 0 || v > 8) return fail(h, SGRACE_EINVAL, "lat_adj not in 0..8"); h->lat_adj = (int)v; break;
+        case SGRACE_OPT_FEA_THREADS: if (v != 1 && v != 2 && v != 4) return fail(h, SGRACE_EINVAL, "fea_threads must be 1,2,4"); h->fea_threads = (int)v; break;
+        case SGRACE_OPT_ADJ_THREADS: if (v != 1 && v != 2 && v != 4) return fail(h, SGRACE_EINVAL, "adj_threads must be 1,2,4"); h->adj_threads = (int)v; break;
+        case SGRACE_OPT_USE_SBLOCKS: h->use_sblocks = v != 0; break;
+        case SGRACE_OPT_INDEX_FORMAT: if (v != 0 && v != 1) return fail(h, SGRACE_EINVAL, "index_format must be 0/1"); h->index_format = (int)v; break;
+        case SGRACE_OPT_QBITS: if (v != 0 && v != 1 && v != 2 && v != 4 && v != 8) return fail(h, SGRACE_EINVAL, "qbits must be 0,1,2,4,8"); h->qbits = (int)v; break;
+        case SGRACE_OPT_STAGING: h->staging = v != 0; break;
+        case SGRACE_OPT_LONG_ROW: if (v < 1) return fail(h, SGRACE_EINVAL, "long_row < 1"); h->long_row = (int)v; break;
+        case SGRACE_OPT_LEAKY_ALPHA_BITS: { uint32_t b = (uint32_t)v; memcpy(&h->leaky_alpha, &b, 4); break; }
+        case SGRACE_OPT_VALIDATE: h->validate = v != 0; break;
+        case SGRACE_OPT_DENSE_TC: h->dense_tc = v != 0; break;
+        default: return fail(h, SGRACE_EINVAL, "unknown option %d", key);
+    }
+    return SGRACE_OK;
+}
+
+int sgrace_get_option(sgrace_handle* h, int key, int64_t* v) {
+    if (!h || !v) return SGRACE_EINVAL;
+    switch (key) {
+        case SGRACE_OPT_MODE: *v = h->mode; break;
+        case SGRACE_OPT_SPMM_BLOCK: *v = h->spmm_block; break;
+        case SGRACE_OPT_LAT_FEA: *v = h->lat_fea; break;
+        case SGRACE_OPT_LAT_ADJ: *v = h->lat_adj; break;
+        case SGRACE_OPT_FEA_THREADS: *v = h->fea_threads; break;
+        case SGRACE_OPT_ADJ_THREADS: *v = h->adj_threads; break;
+        case SGRACE_OPT_USE_SBLOCKS: *v = h->use_sblocks; break;
+        case SGRACE_OPT_INDEX_FORMAT: *v = h->index_format; break;
+        case SGRACE_OPT_QBITS: *v = h->qbits; break;
+        case SGRACE_OPT_STAGING: *v = h->staging; break;
+        case SGRACE_OPT_LONG_ROW: *v = h->long_row; break;
+        case SGRACE_OPT_LEAKY_ALPHA_BITS: { uint32_t b; memcpy(&b, &h->leaky_alpha, 4); *v = b; break; }
+        case SGRACE_OPT_VALIDATE: *v = h->validate; break;
+        case SGRACE_OPT_DENSE_TC: *v = h->dense_tc; break;
+        default: return fail(h, SGRACE_EINVAL, "unknown option %d", key);
+    }
+    return SGRACE_OK;
+}
+
+int sgrace_set_stream(sgrace_handle* h, void* s) {
+    if (!h) return SGRACE_EINVAL;
+    CU(cudaStreamSynchronize(h->stream));
+    if (s) {
+        if (h->own_stream) cudaStreamDestroy(h->stream);
+        h->stream = (cudaStream_t)s;
+        h->own_stream = false;
+    } else if (!h->own_stream) {
+        CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+    }
+    return SGRACE_OK;
+}
+
+int sgrace_layer_run(sgrace_handle* h, const sgrace_layer_desc* d) {
+    if (!h) return SGRACE_EINVAL;
+    CU(cudaSetDevice(h->device));
+    return layer_run_impl(h, d, false);
+}
+
+int sgrace_fea_run(sgrace_handle* h, const sgrace_layer_desc* d, void* XW_out) {
+    if (!h) return SGRACE_EINVAL;
+    CU(cudaSetDevice(h->device));
+    if (int rc = check_desc(h, d)) return rc;
+    if (!XW_out) return fail(h, SGRACE_EINVAL, "XW_out is null");
+    const int *rp_fea, *rp_adj;
+    if (int rc = resolve_rowptrs(h, d, &rp_fea, &rp_adj, true, false)) return rc;
+    return run_fea(h, d, rp_fea, XW_out);
+}
+
+int sgrace_adj_run(sgrace_handle* h, const sgrace_layer_desc* d, const void* XW_in, int32_t xw_rows) {
+    if (!h) return SGRACE_EINVAL;
+    CU(cudaSetDevice(h->device));
+    if (int rc = check_desc(h, d)) return rc;
+    if (!XW_in) return fail(h, SGRACE_EINVAL, "XW_in is null");
+    const int *rp_fea, *rp_adj;
+    if (int rc = resolve_rowptrs(h, d, &rp_fea, &rp_adj, false, true)) return rc;
+    return run_adj(h, d, rp_adj, XW_in, xw_rows);
+}
+
+int sgrace_start(sgrace_handle* h) {
+    if (!h) return SGRACE_EINVAL;
+    CU(cudaSetDevice(h->device));
+    h->last_status = 0;
+    // bias_count > 0 is the parameter-preload-only call of the open design: nothing to compute
+    // (kernelMatrixmult_all.cpp:3876-3888)
+    if ((int32_t)h->regs[SGRACE_REG_BIAS_COUNT / 4] > 0) { h->running = true; h->ev_valid = false;
+        CU(cudaEventRecord(h->ev[3], h->stream)); return SGRACE_OK; }
+
+    sgrace_layer_desc d;
+    memset(&d, 0, sizeof(d));
+    d.gemm_mode = (int32_t)h->regs[SGRACE_REG_GEMM_MODE / 4];
+    d.relu = (int32_t)(h->regs[SGRACE_REG_RELU / 4] & 1u);
+    d.gat_mode = (int32_t)(h->regs[SGRACE_REG_GAT_MODE / 4] & 1u);
+    d.N_adj = (int32_t)h->regs[SGRACE_REG_N_ADJ / 4];
+    d.M_adj = (int32_t)h->regs[SGRACE_REG_M_ADJ / 4];
+    d.M_fea = (int32_t)h->regs[SGRACE_REG_M_FEA / 4];
+    d.P_w = (int32_t)h->regs[SGRACE_REG_P_W / 4];
+    d.nnz_fea = (int32_t)h->regs[SGRACE_REG_NNZ_FEA1 / 4];
+    d.nnz_adj = (int32_t)h->regs[SGRACE_REG_NNZ_ADJ1 / 4];
+    d.scale_fea = (int32_t)h->regs[SGRACE_REG_SCALE_FEA / 4];
+    d.internal_quantization = (int32_t)h->regs[SGRACE_REG_QUANTIZED_MULTIPLIER / 4];
+    d.qscale_fea = regf(h, SGRACE_REG_QSCALE_FEA);
+    d.qscale_w = regf(h, SGRACE_REG_QSCALE_W);
+    d.qscale_adj = regf(h, SGRACE_REG_QSCALE_ADJ);
+    d.deq_factor = regf(h, SGRACE_REG_DEQ_FACTOR);
+    const uint64_t a_rpf = reg64(h, SGRACE_REG_ROWPTR_FEA1), a_cif = reg64(h, SGRACE_REG_COLIDX_FEA1),
+                   a_vf = reg64(h, SGRACE_REG_VALUES_FEA1), a_rpa = reg64(h, SGRACE_REG_ROWPTR_ADJ1),
+                   a_cia = reg64(h, SGRACE_REG_COLIDX_ADJ1), a_va = reg64(h, SGRACE_REG_VALUES_ADJ1),
+                   a_b = reg64(h, SGRACE_REG_B), a_d = reg64(h, SGRACE_REG_D1), a_e = reg64(h, SGRACE_REG_E1),
+                   a_s = reg64(h, SGRACE_REG_S1), a_att = reg64(h, SGRACE_REG_ATE_M);
+    d.rowPtr_fea = (const int32_t*)(uintptr_t)a_rpf;
+    d.columnIndex_fea = (const int32_t*)(uintptr_t)a_cif;
+    d.values_fea = (const void*)(uintptr_t)a_vf;
+    d.rowPtr_adj = (const int32_t*)(uintptr_t)a_rpa;
+    d.columnIndex_adj = (const int32_t*)(uintptr_t)a_cia;
+    d.values_adj = (const void*)(uintptr_t)a_va;
+    d.B = (const void*)(uintptr_t)a_b;
+    d.D = (void*)(uintptr_t)a_d;
+    const bool full = h->mode == SGRACE_MODE_FULL;
+    const bool gat = full && d.gat_mode;
+    d.attention = gat ? (const float*)(uintptr_t)a_att : nullptr;
+    d.E = gat ? (float*)(uintptr_t)a_e : nullptr;
+    d.S = gat ? (float*)(uintptr_t)a_s : nullptr;
+    if (int rc = check_desc(h, &d)) return rc;
+
+    const size_t esz = elt_bytes(h->mode);
+    const size_t N = (size_t)d.N_adj, M = (size_t)d.M_fea, P = (size_t)d.P_w;
+    // non-zero counts: registers (COO format) or the last row pointer read from the host mirror
+    long long nnz_fea = d.nnz_fea, nnz_adj = d.nnz_adj;
+    if (h->index_format == 0) {
+        // true CSR: the count is the last row pointer -- read from the host mirror when there is
+        // one (bounds-checked), else from the device
+        auto last_ptr = [&](uint64_t addr, const int32_t* dptr, long long* out) -> int {
+            size_t off;
+            const Buffer* b = find_buffer(h, addr, &off);
+            if (b && off + (N + 1) * 4 > b->bytes)
+                return fail(h, SGRACE_EBOUNDS, "rowPtr buffer holds %zu bytes but N_adj=%zu needs %zu", b->bytes - off,
+                            N, (N + 1) * 4);
+            if (h->staging && b) { *out = ((const int*)((const char*)b->host + off))[N]; return 0; }
+            if (*out <= 0 && dptr && N) {
+                int v = 0;
+                CU(cudaMemcpyAsync(&v, dptr + N, 4, cudaMemcpyDeviceToHost, h->stream));
+                CU(cudaStreamSynchronize(h->stream));
+                *out = v;
+            }
+            return 0;
+        };
+        if (int rc = last_ptr(a_rpa, d.rowPtr_adj, &nnz_adj)) return rc;
+        if (d.gemm_mode == 0) if (int rc = last_ptr(a_rpf, d.rowPtr_fea, &nnz_fea)) return rc;
+        d.nnz_adj = (int32_t)nnz_adj;
+        d.nnz_fea = (int32_t)nnz_fea;
+    }
+    if (nnz_adj < 0 || nnz_fea < 0) return fail(h, SGRACE_EBOUNDS, "negative non-zero count");
+
+    if (h->validate && h->staging && h->index_format == 0) {
+        auto span_ok = [&](uint64_t addr, size_t bytes) {
+            size_t off;
+            const Buffer* b = find_buffer(h, addr, &off);
+            return b && off + bytes <= b->bytes;
+        };
+        if (span_ok(a_rpa, (N + 1) * 4) && span_ok(a_cia, (size_t)nnz_adj * 4))
+            if (int rc = validate_csr_host(h, (const int*)host_view(h, a_rpa), (const int*)host_view(h, a_cia),
+                                           (int)N, (int)N, "adjacency")) return rc;
+        if (d.gemm_mode == 0 && span_ok(a_rpf, (N + 1) * 4) && span_ok(a_cif, (size_t)nnz_fea * 4))
+            if (int rc = validate_csr_host(h, (const int*)host_view(h, a_rpf), (const int*)host_view(h, a_cif),
+                                           (int)N, (int)M, "features")) return rc;
+    }
+
+    CU(cudaEventRecord(h->ev[4], h->stream));
+    if (h->staging) {
+        // host mirror -> device, only the ranges this layer reads
+        const size_t rp_bytes_a = h->index_format == 0 ? (N + 1) * 4 : (size_t)nnz_adj * 4;
+        if (int rc = stage_in(h, a_rpa, rp_bytes_a)) return rc;
+        if (int rc = stage_in(h, a_cia, (size_t)nnz_adj * 4)) return rc;
+        if (int rc = stage_in(h, a_va, (size_t)nnz_adj * esz)) return rc;
+        if (d.gemm_mode == 0) {
+            const size_t rp_bytes_f = h->index_format == 0 ? (N + 1) * 4 : (size_t)nnz_fea * 4;
+            if (int rc = stage_in(h, a_rpf, rp_bytes_f)) return rc;
+            if (int rc = stage_in(h, a_cif, (size_t)nnz_fea * 4)) return rc;
+            if (int rc = stage_in(h, a_vf, (size_t)nnz_fea * esz)) return rc;
+        } else {
+            if (int rc = stage_in(h, a_vf, N * M * esz)) return rc;
+        }
+        if (int rc = stage_in(h, a_b, M * P * esz)) return rc;
+        if (gat) if (int rc = stage_in(h, a_att, 2 * P * 4)) return rc;
+    }
+
+    h->ev_valid = false;
+    if (int rc = layer_run_impl(h, &d, true)) return rc;
+
+    if (full && h->qbits > 0 && h->max_fea_dev) {
+        // max |X_q W_q| as a 16-fractional-bit integer (sgrace.py:506-520 divides by 2^frac_bits_o)
+        int m = 0;
+        CU(cudaMemcpyAsync(&m, h->max_fea_dev, 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        const double den = (h->qbits == 1 ? 2.0 : (double)(1 << (h->qbits - 1)));
+        double v = (double)m / (den * den) * 65536.0;
+        h->regs[SGRACE_REG_MAX_FEA / 4] = v > 2147483647.0 ? 2147483647u : (uint32_t)v;
+    }
+    if (h->staging) {
+        if (int rc = stage_out(h, a_d, N * P * esz)) return rc;
+        if (gat) {
+            if (int rc = stage_out(h, a_e, (size_t)nnz_adj * 4)) return rc;
+            if (int rc = stage_out(h, a_s, (size_t)nnz_adj * 4)) return rc;
+        }
+        // the open design's FIFO counters read 0 as built (mmult-master.ipynb cells 39-40)
+        const uint64_t a_prof = reg64(h, SGRACE_REG_PROFILING);
+        size_t off;
+        const Buffer* pb = find_buffer(h, a_prof, &off);
+        if (pb && off + 15 * 8 <= pb->bytes) memset((char*)pb->host + off, 0, 15 * 8);
+    }
+    CU(cudaEventRecord(h->ev[3], h->stream));
+    h->ev_valid = true;
+    h->running = true;
+    return SGRACE_OK;
+}
+
+int sgrace_done(sgrace_handle* h, int* done) {
+    if (!h || !done) return SGRACE_EINVAL;
+    if (!h->running) { *done = 0; return SGRACE_OK; }
+    cudaError_t e = cudaEventQuery(h->ev[3]);
+    if (e == cudaSuccess) { *done = 1; return SGRACE_OK; }
+    if (e == cudaErrorNotReady) { *done = 0; return SGRACE_OK; }
+    *done = 1;
+    return fail(h, SGRACE_ECUDA, "layer failed: %s", cudaGetErrorString(e));
+}
+
+int sgrace_wait(sgrace_handle* h) {
+    if (!h) return SGRACE_EINVAL;
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return h->last_status;
+}
+
+int sgrace_stage_times(sgrace_handle* h, float* fea_ms, float* adj_ms, float* total_ms) {
+    if (!h) return SGRACE_EINVAL;
+    if (!h->ev_valid) return fail(h, SGRACE_EINVAL, "no completed layer to time");
+    CU(cudaEventSynchronize(h->ev[3]));
+    float a = 0, b = 0, c = 0;
+    CU(cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
+    CU(cudaEventElapsedTime(&b, h->ev[1], h->ev[2]));
+    CU(cudaEventElapsedTime(&c, h->ev[4], h->ev[3]));
+    if (fea_ms) *fea_ms = a;
+    if (adj_ms) *adj_ms = b;
+    if (total_ms) *total_ms = c;
+    return SGRACE_OK;
+}
+
+int sgrace_launch_count(sgrace_handle* h, uint64_t* count) {
+    if (!h || !count) return SGRACE_EINVAL;
+    *count = h->launches;
+    return SGRACE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,647 @@
+// sgrace_kernels.cuh -- sm_100a device kernels for the SGRACE fused graph layer
+//   D = act( A . (X . W) )      FEA stage: XW = X.W     ADJ stage: D = A.XW
+//
+// Reference behaviour being replaced (not ported): the HLS dataflow kernel
+//   gnn-rfsoc-mt-all-2022/src/kernelMatrixmult_all.cpp  (cited K:line)
+//   loop_fea K:2932-3336, loop_adj K:3339-3627, dsp_kernel_wrapper_* K:1413-2152
+// and the full-design semantics stated by demo/sgrace_lib/sgrace.py:563-681 (S:line).
+//
+// Every stage here is HBM/L2-bound gather work, so the kernels are CUDA-core code built
+// around coalesced 128-bit row loads, sub-warp row groups and warp shuffles; nothing is
+// reshaped into a GEMM.  The one real contraction (dense FEA with a wide hidden layer)
+// lives in sgrace_gemm_tc.cuh.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sgrace {
+
+// ---------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+__device__ __forceinline__ void fma4(float4& a, float s, const float4& b) {
+    a.x = fmaf(s, b.x, a.x); a.y = fmaf(s, b.y, a.y);
+    a.z = fmaf(s, b.z, a.z); a.w = fmaf(s, b.w, a.w);
+}
+
+// streaming store: D / XW rows are written once and not re-read by this kernel
+__device__ __forceinline__ void st_cs4(float4* p, const float4& v) { __stcs(p, v); }
+
+// ---------------------------------------------------------------------------------
+// W staging: the B buffer holds W TRANSPOSED, B[i + j*M] = W[i][j]  (K:3038-3051,
+// main_float.cpp:180, sgrace.py:430-459).  Every kernel below wants W row-major so that
+// one row of W is one contiguous 128-bit-loadable segment.
+// ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void transpose_b_kernel(const T* __restrict__ B, T* __restrict__ Wrm, int M, int P) {
+    __shared__ T tile[32][33];
+    int m0 = blockIdx.x * 32, p0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int p = p0 + j, m = m0 + threadIdx.x;
+        if (p < P && m < M) tile[j][threadIdx.x] = B[(size_t)p * M + m];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int m = m0 + j, p = p0 + threadIdx.x;
+        if (m < M && p < P) Wrm[(size_t)m * P + p] = tile[threadIdx.x][j];
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// COO row indices -> CSR row pointer.  The full-design driver stores COO *row indices*
+// (sorted) in the rowPtr buffers and passes nnz in registers (S:1222, S:1245, S:1221);
+// the open design stores true CSR pointers (Graph_Classification.ipynb cell 18:62-63).
+// ---------------------------------------------------------------------------------
+__global__ void coo_rows_to_rowptr_kernel(const int* __restrict__ rows, int nnz, int n,
+                                          int* __restrict__ rowptr) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n) return;
+    int lo = 0, hi = nnz;           // first k with rows[k] >= r
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(rows + mid) < r) lo = mid + 1; else hi = mid;
+    }
+    rowptr[r] = lo;
+}
+
+// ---------------------------------------------------------------------------------
+// Fast float32 CSR x row-major SpMM   out[r,:] = act( sum_k val[k] * Bm[col[k],:] )
+//
+// Used for both stages: FEA-sparse (X_csr . W) and ADJ (A_csr . XW, fused ReLU,
+// K:2586-2590).  Layout: a row of Bm is P floats = P/4 float4; a *row group* of LPR
+// lanes owns one CSR row, lane l holding columns {(v*LPR + l)*4 .. +3}, so one gathered
+// Bm row is one coalesced 16*LPR-byte request.  32/LPR consecutive CSR rows share a
+// warp (the sblock idea of K:1818-1861: short rows are processed together so the
+// pipeline never drains per row), and the group streams its non-zeros STEP at a time:
+// STEP lanes fetch (col,val) with one request, the group broadcasts them by shuffle and
+// keeps STEP independent Bm-row loads in flight.  Rows longer than `long_thresh` are
+// skipped here and handled by spmm_long_rows_f32 (row-bucket scheduling for power-law
+// graphs).  Accumulation is float FMA in CSR order per row: deterministic, no atomics.
+// ---------------------------------------------------------------------------------
+template <int LPR, int NV>
+__global__ void __launch_bounds__(256)
+spmm_csr_f32_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+                    const float* __restrict__ val, const float4* __restrict__ Bm,
+                    float4* __restrict__ out, int nrows, int P4, int relu, int long_thresh,
+                    int* __restrict__ long_rows, int* __restrict__ long_count) {
+    constexpr int RPW = 32 / LPR;                 // rows per warp
+    constexpr int STEP = LPR < 8 ? LPR : 8;       // non-zeros fetched per group request
+    const int lane = threadIdx.x & 31;
+    const int g = lane / LPR, l = lane % LPR;
+    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (g * LPR));
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+
+    for (long long w = warp0; w * RPW < nrows; w += nwarps) {
+        const int row = (int)(w * RPW) + g;
+        if (row >= nrows) continue;               // whole group leaves together
+        int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+        if (end - beg > long_thresh) {            // defer to the long-row kernel
+            if (l == 0) long_rows[atomicAdd(long_count, 1)] = row;
+            continue;
+        }
+        float4 acc[NV];
+#pragma unroll
+        for (int v = 0; v < NV; v++) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+        for (int k = beg; k < end; k += STEP) {
+            int c = 0; float a = 0.f;
+            if (l < STEP && k + l < end) { c = __ldg(col + k + l); a = __ldg(val + k + l); }
+#pragma unroll
+            for (int i = 0; i < STEP; i++) {
+                const int ci = __shfl_sync(gmask, c, g * LPR + i);
+                const float ai = __shfl_sync(gmask, a, g * LPR + i);
+                if (k + i < end) {
+                    const float4* brow = Bm + (size_t)ci * P4;
+#pragma unroll
+                    for (int v = 0; v < NV; v++) {
+                        const int q = v * LPR + l;
+                        if (NV * LPR == P4 || q < P4) fma4(acc[v], ai, ldg4(brow + q));
+                    }
+                }
+            }
+        }
+        float4* orow = out + (size_t)row * P4;
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+            const int q = v * LPR + l;
+            if (NV * LPR == P4 || q < P4) {
+                float4 r = acc[v];
+                if (relu) {   // val = (acc > 0 || relu == 0) ? acc : 0   (K:2586-2590)
+                    r.x = r.x > 0.f ? r.x : 0.f; r.y = r.y > 0.f ? r.y : 0.f;
+                    r.z = r.z > 0.f ? r.z : 0.f; r.w = r.w > 0.f ? r.w : 0.f;
+                }
+                st_cs4(orow + q, r);
+            }
+        }
+    }
+}
+
+// Long rows: one CTA per listed row.  Each warp walks a contiguous slice of the row's
+// non-zeros; lanes own float4 column chunks (q = lane, lane+32, ...), warps' partials
+// are combined in warp order through shared memory -> deterministic.
+template <int NV>
+__global__ void __launch_bounds__(256)
+spmm_long_rows_f32_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+                          const float* __restrict__ val, const float4* __restrict__ Bm,
+                          float4* __restrict__ out, int P4, int relu,
+                          const int* __restrict__ long_rows, const int* __restrict__ long_count) {
+    extern __shared__ float4 red[];               // [nwarp][P4]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int total = *long_count;
+    for (int idx = blockIdx.x; idx < total; idx += gridDim.x) {
+        const int row = long_rows[idx];
+        const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+        const int len = end - beg, per = (len + nw - 1) / nw;
+        const int kb = beg + wid * per, ke = min(end, kb + per);
+        float4 acc[NV];
+#pragma unroll
+        for (int v = 0; v < NV; v++) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = kb; k < ke; k += 32) {
+            int c = 0; float a = 0.f;
+            if (k + lane < ke) { c = __ldg(col + k + lane); a = __ldg(val + k + lane); }
+            const int cnt = min(32, ke - k);
+            for (int i = 0; i < cnt; i++) {
+                const int ci = __shfl_sync(0xffffffffu, c, i);
+                const float ai = __shfl_sync(0xffffffffu, a, i);
+                const float4* brow = Bm + (size_t)ci * P4;
+#pragma unroll
+                for (int v = 0; v < NV; v++) {
+                    const int q = v * 32 + lane;
+                    if (q < P4) fma4(acc[v], ai, ldg4(brow + q));
+                }
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+            const int q = v * 32 + lane;
+            if (q < P4) red[wid * P4 + q] = acc[v];
+        }
+        __syncthreads();
+        for (int q = threadIdx.x; q < P4; q += blockDim.x) {
+            float4 r = red[q];
+            for (int w2 = 1; w2 < nw; w2++) {
+                const float4 t = red[w2 * P4 + q];
+                r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w;
+            }
+            if (relu) {
+                r.x = r.x > 0.f ? r.x : 0.f; r.y = r.y > 0.f ? r.y : 0.f;
+                r.z = r.z > 0.f ? r.z : 0.f; r.w = r.w > 0.f ? r.w : 0.f;
+            }
+            out[(size_t)row * P4 + q] = r;
+        }
+        __syncthreads();
+    }
+}
+
+// Generic-width fallback (P not a multiple of 4, e.g. the reference's P_w = 21 tail
+// case, K:794-799): a full warp per row, lane j owns columns j, j+32, ...
+template <int NC>
+__global__ void __launch_bounds__(256)
+spmm_csr_f32_scalar_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+                           const float* __restrict__ val, const float* __restrict__ Bm,
+                           float* __restrict__ out, int nrows, int P, int relu) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long row = warp0; row < nrows; row += nwarps) {
+        const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+        float acc[NC];
+#pragma unroll
+        for (int v = 0; v < NC; v++) acc[v] = 0.f;
+        for (int k = beg; k < end; k += 32) {
+            int c = 0; float a = 0.f;
+            if (k + lane < end) { c = __ldg(col + k + lane); a = __ldg(val + k + lane); }
+            const int cnt = min(32, end - k);
+            for (int i = 0; i < cnt; i++) {
+                const int ci = __shfl_sync(0xffffffffu, c, i);
+                const float ai = __shfl_sync(0xffffffffu, a, i);
+                const float* brow = Bm + (size_t)ci * P;
+#pragma unroll
+                for (int v = 0; v < NC; v++) {
+                    const int j = v * 32 + lane;
+                    if (j < P) acc[v] = fmaf(ai, __ldg(brow + j), acc[v]);
+                }
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < NC; v++) {
+            const int j = v * 32 + lane;
+            if (j < P) out[(size_t)row * P + j] = (relu && !(acc[v] > 0.f)) ? 0.f : acc[v];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Dense FEA on CUDA cores (gemm_mode = 1, K:847-865 / K:985-1013): XW = X . W with X
+// dense row-major N x M (zeros included).  64x64 output tile per CTA, 4x4 per thread,
+// K-slab of 16 through shared memory.  Used when the contraction is too small for the
+// tensor pipe (M = 7, 16, 64 ...) and as the always-correct path for any shape.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fea_dense_f32_kernel(const float* __restrict__ X, const float* __restrict__ Wrm,
+                     float* __restrict__ out, int N, int M, int P) {
+    __shared__ float xs[16][64 + 4];
+    __shared__ float ws[16][64 + 4];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < M; k0 += 16) {
+        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+            int rr = i >> 4, kk = i & 15;            // X tile: 64 rows x 16 k (k fastest: coalesced)
+            int r = r0 + rr, k = k0 + kk;
+            xs[kk][rr] = (r < N && k < M) ? __ldg(X + (size_t)r * M + k) : 0.f;
+        }
+        for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+            int kk = i >> 6, cc = i & 63;
+            int k = k0 + kk, c = c0 + cc;
+            ws[kk][cc] = (k < M && c < P) ? __ldg(Wrm + (size_t)k * P + c) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; kk++) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = xs[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; j++) b[j] = ws[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int r = r0 + ty * 4 + i;
+        if (r >= N) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int c = c0 + tx * 4 + j;
+            if (c < P) out[(size_t)r * P + c] = acc[i][j];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Bit-exact "C-simulation order" kernels.
+//
+// One thread per (row, column).  The thread walks the row's stream positions in order
+// and reproduces the reference accumulate order exactly: product rounded, added into
+// partial accumulator lane (stream position % LAT) (K:2009-2042), lanes folded
+// 1..LAT-1 into lane 0 (K:2050-2061); stream positions count from the start of the
+// row's sblock, which restarts at every hardware thread's first row (K:3159-3164,
+// K:3585-3594).  Arithmetic policies:
+//   OpsF32  : FLOAT build (H:141-151) -- IEEE mul then add, never fused
+//   OpsF16  : HALF build (H:129-139)  -- binary16 RNE with denormals flushed to zero,
+//             the Xilinx Floating-Point Operator behaviour pinned by the golden vectors
+//   OpsFix16: EIGHTBIT build (H:105-109) -- ap_fixed<16,2> AP_TRN/AP_WRAP, one accumulator
+// Lanes of a warp cover consecutive columns, so Bm rows are read coalesced.
+// ---------------------------------------------------------------------------------
+struct OpsF32 {
+    typedef float T;
+    static __device__ __forceinline__ T zero() { return 0.f; }
+    static __device__ __forceinline__ T mul(T a, T b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ T add(T a, T b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ bool gt0(T a) { return a > 0.f; }
+};
+struct OpsF16 {
+    typedef unsigned short T;
+    static __device__ __forceinline__ T zero() { return 0; }
+    static __device__ __forceinline__ T mul(T a, T b) {
+        T d; asm("mul.rn.ftz.f16 %0, %1, %2;" : "=h"(d) : "h"(a), "h"(b)); return d;
+    }
+    static __device__ __forceinline__ T add(T a, T b) {
+        T d; asm("add.rn.ftz.f16 %0, %1, %2;" : "=h"(d) : "h"(a), "h"(b)); return d;
+    }
+    static __device__ __forceinline__ bool gt0(T a) {
+        return __half2float(__ushort_as_half(a)) > 0.f;
+    }
+};
+struct OpsFix16 {
+    typedef short T;
+    static __device__ __forceinline__ T zero() { return 0; }
+    static __device__ __forceinline__ T mul(T a, T b) { return (short)(((int)a * (int)b) >> 14); }
+    static __device__ __forceinline__ T add(T a, T b) { return (short)((int)a + (int)b); }
+    static __device__ __forceinline__ bool gt0(T a) { return a > 0; }
+};
+
+template <typename Ops, int LAT>
+__global__ void __launch_bounds__(256)
+stage_exact_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+                   const typename Ops::T* __restrict__ val,
+                   const typename Ops::T* __restrict__ Bm,   // row-major, row stride P
+                   typename Ops::T* __restrict__ out, int nrows, int P,
+                   int hw_threads, int sblock, int dense_M, int relu) {
+    typedef typename Ops::T T;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)nrows * P) return;
+    const int r = (int)(gid / P), j = (int)(gid % P);
+    // hardware-thread slice and sblock that contain row r
+    const int blk = nrows / hw_threads;
+    int t = blk > 0 ? r / blk : hw_threads - 1;
+    if (t > hw_threads - 1) t = hw_threads - 1;
+    const int first_row = t * blk;
+    const int base_row = first_row + ((r - first_row) / sblock) * sblock;
+    long long beg, end, base;
+    if (dense_M > 0) {                           // gemm_mode: every row streams M entries
+        beg = (long long)r * dense_M; end = beg + dense_M; base = (long long)base_row * dense_M;
+    } else {
+        beg = rowptr[r]; end = rowptr[r + 1]; base = rowptr[base_row];
+    }
+    T part[LAT];
+#pragma unroll
+    for (int i = 0; i < LAT; i++) part[i] = Ops::zero();
+    int lane = (int)((beg - base) % LAT);
+    for (long long k = beg; k < end; k++) {
+        const T v = val[k];
+        const long long ci = dense_M > 0 ? (k - beg) : (long long)col[k];
+        const T prod = Ops::mul(v, Bm[ci * P + j]);
+#pragma unroll
+        for (int i = 0; i < LAT; i++)
+            if (i == lane) part[i] = Ops::add(part[i], prod);
+        lane = (lane + 1 == LAT) ? 0 : lane + 1;
+    }
+    T acc = part[0];
+#pragma unroll
+    for (int i = 1; i < LAT; i++) acc = Ops::add(acc, part[i]);
+    if (relu && !Ops::gt0(acc)) acc = Ops::zero();
+    out[(long long)r * P + j] = acc;
+}
+
+// ---------------------------------------------------------------------------------
+// Full-design (quantised / GAT) kernels, semantics of the emulation S:563-681.
+// ---------------------------------------------------------------------------------
+struct QConst {
+    float inv_fs, inv_ws, inv_as;   // float(1/s)
+    int f_z, w_z, a_z;
+    int qbits;                      // 8,4,2,1
+    float den;                      // 2^(q-1), or 2 for q == 1
+    float wh_den;                   // den*den
+    float wh_scale;                 // 2^scale_fea
+    float a_hi;                     // (2^iq - 1)/2^iq
+    float round_T;                  // (float)10^(iq-1)
+    float deq_o;
+    float alpha;
+};
+
+__device__ __forceinline__ int q_code_unsigned(float x, float inv_s, int z, int qbits) {
+    // quantization_ufbits S:253-265: torch.round = round-half-even
+    float r = rintf(__fadd_rn(__fmul_rn(inv_s, x), (float)z));
+    const float hi = (float)((1 << qbits) - 1);
+    r = r < 0.f ? 0.f : r;
+    r = r > hi ? hi : r;
+    return (int)r;
+}
+__device__ __forceinline__ int q_code_signed(float x, float inv_s, int z, int qbits) {
+    // quantization_fbits S:238-251; 1 bit -> sign (fake_quantization_b S:177-182)
+    const float t = __fadd_rn(__fmul_rn(inv_s, x), (float)z);
+    if (qbits == 1) return t < 0.f ? -1 : 1;
+    float r = rintf(t);
+    const float hi = (float)((1 << (qbits - 1)) - 1);
+    r = r < -hi ? -hi : r;
+    r = r > hi ? hi : r;
+    return (int)r;
+}
+
+// W (B buffer, P x M float) -> int8 codes, row-major M x Pp (Pp = P padded to 4)
+__global__ void quantize_w_kernel(const float* __restrict__ B, signed char* __restrict__ Wq,
+                                  int M, int P, int Pp, QConst qc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * Pp) return;
+    const int m = i / Pp, p = i % Pp;
+    Wq[i] = (p < P) ? (signed char)q_code_signed(B[(size_t)p * M + m], qc.inv_ws, qc.w_z, qc.qbits) : 0;
+}
+
+__device__ __forceinline__ float wh_rescale(int acc, const QConst& qc) {
+    // Wh = (X_q W_q) / 2^scale_fea, clip, torch.round(decimals = iq-1)   (S:601-616)
+    float wh = __fdiv_rn((float)acc, qc.wh_den);
+    wh = __fdiv_rn(wh, qc.wh_scale);
+    wh = wh < -qc.a_hi ? -qc.a_hi : wh;
+    wh = wh > qc.a_hi ? qc.a_hi : wh;
+    return __fdiv_rn(rintf(__fmul_rn(wh, qc.round_T)), qc.round_T);
+}
+
+// FEA, quantised, sparse X: integer MACs (exact), fixed-point rescale epilogue.
+// One thread per (row, 4 columns): the 4 int8 weight codes of a W row are one 32-bit load.
+__global__ void __launch_bounds__(256)
+fea_q_csr_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+                 const float* __restrict__ val, const signed char* __restrict__ Wq,
+                 float* __restrict__ Wh, int nrows, int P, int Pp, QConst qc,
+                 int* __restrict__ max_fea) {
+    const int P4 = Pp >> 2;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int lmax = 0;
+    if (gid < (long long)nrows * P4) {
+        const int r = (int)(gid / P4), q = (int)(gid % P4);
+        int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        const int beg = rowptr[r], end = rowptr[r + 1];
+        for (int k = beg; k < end; k++) {
+            const int xi = q_code_unsigned(__ldg(val + k), qc.inv_fs, qc.f_z, qc.qbits);
+            const int w = __ldg(reinterpret_cast<const int*>(Wq + (size_t)__ldg(col + k) * Pp) + q);
+            a0 += xi * (int)(signed char)(w & 0xff);
+            a1 += xi * (int)(signed char)((w >> 8) & 0xff);
+            a2 += xi * (int)(signed char)((w >> 16) & 0xff);
+            a3 += xi * (int)(signed char)((w >> 24) & 0xff);
+        }
+        const int a[4] = {a0, a1, a2, a3};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int j = q * 4 + i;
+            if (j < P) {
+                Wh[(size_t)r * P + j] = wh_rescale(a[i], qc);
+                lmax = max(lmax, abs(a[i]));
+            }
+        }
+    }
+    if (max_fea) {
+        for (int o = 16; o; o >>= 1) lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        if ((threadIdx.x & 31) == 0 && lmax) atomicMax(max_fea, lmax);
+    }
+}
+
+// FEA, quantised, dense X (gemm_mode = 1): X codes computed on the fly, dp4a over 4 features
+// is not applicable (W codes are laid out per feature row), so plain integer MACs.
+__global__ void __launch_bounds__(256)
+fea_q_dense_kernel(const float* __restrict__ X, const signed char* __restrict__ Wq,
+                   float* __restrict__ Wh, int nrows, int M, int P, int Pp, QConst qc,
+                   int* __restrict__ max_fea) {
+    const int P4 = Pp >> 2;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int lmax = 0;
+    if (gid < (long long)nrows * P4) {
+        const int r = (int)(gid / P4), q = (int)(gid % P4);
+        int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        for (int m = 0; m < M; m++) {
+            const int xi = q_code_unsigned(__ldg(X + (size_t)r * M + m), qc.inv_fs, qc.f_z, qc.qbits);
+            const int w = __ldg(reinterpret_cast<const int*>(Wq + (size_t)m * Pp) + q);
+            a0 += xi * (int)(signed char)(w & 0xff);
+            a1 += xi * (int)(signed char)((w >> 8) & 0xff);
+            a2 += xi * (int)(signed char)((w >> 16) & 0xff);
+            a3 += xi * (int)(signed char)((w >> 24) & 0xff);
+        }
+        const int a[4] = {a0, a1, a2, a3};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int j = q * 4 + i;
+            if (j < P) {
+                Wh[(size_t)r * P + j] = wh_rescale(a[i], qc);
+                lmax = max(lmax, abs(a[i]));
+            }
+        }
+    }
+    if (max_fea) {
+        for (int o = 16; o; o >>= 1) lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        if ((threadIdx.x & 31) == 0 && lmax) atomicMax(max_fea, lmax);
+    }
+}
+
+// ADJ, quantised GCN: out = relu( sum_k A_q[k] * Wh[col[k],:] ) * deq_o.  Adjacency codes
+// are formed on the fly; zero codes are the pruned edges (S:626-629) and are skipped.
+// One thread per (row, column), float multiply then add in CSR order (the oracle's order).
+__global__ void __launch_bounds__(256)
+adj_q_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+                 const float* __restrict__ val, const float* __restrict__ Wh,
+                 float* __restrict__ out, int nrows, int P, int relu, int quant, QConst qc) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)nrows * P) return;
+    const int r = (int)(gid / P), j = (int)(gid % P);
+    float acc = 0.f;
+    const int beg = rowptr[r], end = rowptr[r + 1];
+    for (int k = beg; k < end; k++) {
+        float a = __ldg(val + k);
+        if (quant) a = __fdiv_rn((float)q_code_unsigned(a, qc.inv_as, qc.a_z, qc.qbits), qc.den);
+        if (quant && a == 0.f) continue;
+        acc = __fadd_rn(acc, __fmul_rn(a, __ldg(Wh + (size_t)__ldg(col + k) * P + j)));
+    }
+    if (relu && !(acc > 0.f)) acc = 0.f;
+    if (quant) acc = __fmul_rn(acc, qc.deq_o);
+    out[(size_t)r * P + j] = acc;
+}
+
+// GAT scores: s1[i] = Wh[i,:] . a[:P], s2[i] = Wh[i,:] . a[P:]   (S:309-314); the attention
+// vector is quantised with the weight quantiser first (S:624).
+__global__ void __launch_bounds__(256)
+gat_scores_kernel(const float* __restrict__ Wh, const float* __restrict__ att, float* __restrict__ s1,
+                  float* __restrict__ s2, int nrows, int P, int quant, QConst qc) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    float a = 0.f, b = 0.f;
+    for (int j = 0; j < P; j++) {
+        float a1 = __ldg(att + j), a2 = __ldg(att + P + j);
+        if (quant) {
+            a1 = __fdiv_rn((float)q_code_signed(a1, qc.inv_ws, qc.w_z, qc.qbits), qc.den);
+            a2 = __fdiv_rn((float)q_code_signed(a2, qc.inv_ws, qc.w_z, qc.qbits), qc.den);
+        }
+        const float w = Wh[(size_t)r * P + j];
+        a = __fadd_rn(a, __fmul_rn(w, a1));
+        b = __fadd_rn(b, __fmul_rn(w, a2));
+    }
+    s1[r] = a; s2[r] = b;
+}
+
+// GAT edge softmax + aggregation (S:634-650): per row, over surviving edges (A_q > 0):
+// e = LeakyReLU(s1[i] + s2[j]); att = softmax_row(e); out = sum att * Wh[j,:].
+// Writes E (logits) and S (attention) per non-zero in adjacency order (S:500-502).
+// One warp per row; lanes stride the row for max / sum (shuffle reductions), then lanes
+// own columns for the aggregation.  Rows without a surviving edge get the column mean of
+// Wh -- what the dense emulation's uniform softmax over -9e15 logits produces (S:638-641).
+__global__ void __launch_bounds__(256)
+gat_aggregate_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+                     const float* __restrict__ val, const float* __restrict__ Wh,
+                     const float* __restrict__ s1, const float* __restrict__ s2,
+                     float* __restrict__ out, float* __restrict__ E, float* __restrict__ S,
+                     int nrows, int P, int relu, int quant, QConst qc,
+                     int* __restrict__ empty_rows, int* __restrict__ empty_count) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long row = warp0; row < nrows; row += nwarps) {
+        const int beg = rowptr[row], end = rowptr[row + 1];
+        const float si = s1[row];
+        float mx = -INFINITY;
+        int live = 0;
+        for (int k = beg + lane; k < end; k += 32) {
+            float a = __ldg(val + k);
+            if (quant) a = (float)q_code_unsigned(a, qc.inv_as, qc.a_z, qc.qbits);
+            float e = 0.f;
+            if (a > 0.f) {
+                e = __fadd_rn(si, __ldg(s2 + __ldg(col + k)));
+                e = e > 0.f ? e : __fmul_rn(qc.alpha, e);
+                mx = fmaxf(mx, e);
+                live++;
+            }
+            if (E) E[k] = e;
+        }
+        for (int o = 16; o; o >>= 1) {
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            live += __shfl_xor_sync(0xffffffffu, live, o);
+        }
+        if (live == 0) {
+            if (lane == 0) empty_rows[atomicAdd(empty_count, 1)] = (int)row;
+            for (int k = beg + lane; k < end; k += 32) if (S) S[k] = 0.f;
+            continue;
+        }
+        float sum = 0.f;
+        for (int k = beg + lane; k < end; k += 32) {
+            float a = __ldg(val + k);
+            if (quant) a = (float)q_code_unsigned(a, qc.inv_as, qc.a_z, qc.qbits);
+            if (a > 0.f) {
+                float e = __fadd_rn(si, __ldg(s2 + __ldg(col + k)));
+                e = e > 0.f ? e : __fmul_rn(qc.alpha, e);
+                sum += expf(e - mx);
+            }
+        }
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        // aggregation: lanes own columns j = lane, lane+32, ...; edges walked in order
+        for (int j0 = 0; j0 < P; j0 += 32) {
+            const int j = j0 + lane;
+            float acc = 0.f;
+            for (int k = beg; k < end; k++) {
+                float a = __ldg(val + k);
+                if (quant) a = (float)q_code_unsigned(a, qc.inv_as, qc.a_z, qc.qbits);
+                float s = 0.f;
+                if (a > 0.f) {
+                    const int c = __ldg(col + k);
+                    float e = __fadd_rn(si, __ldg(s2 + c));
+                    e = e > 0.f ? e : __fmul_rn(qc.alpha, e);
+                    s = expf(e - mx) / sum;
+                    if (j < P) acc = fmaf(s, __ldg(Wh + (size_t)c * P + j), acc);
+                }
+                if (j0 == 0 && lane == 0 && S) S[k] = s;
+            }
+            if (j < P) {
+                if (relu && !(acc > 0.f)) acc = 0.f;
+                if (quant) acc = __fmul_rn(acc, qc.deq_o);
+                out[(size_t)row * P + j] = acc;
+            }
+        }
+    }
+}
+
+// Column mean of Wh for rows without surviving edges; runs only if any were flagged.
+__global__ void gat_empty_rows_kernel(const float* __restrict__ Wh, float* __restrict__ out,
+                                      int nrows, int P, int relu, int quant, QConst qc,
+                                      const int* __restrict__ empty_rows,
+                                      const int* __restrict__ empty_count) {
+    const int cnt = *empty_count;
+    if (cnt == 0) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P) return;
+    double acc = 0.0;
+    for (int i = 0; i < nrows; i++) acc += (double)Wh[(size_t)i * P + j];
+    float m = (float)(acc / (double)nrows);
+    if (relu && !(m > 0.f)) m = 0.f;
+    if (quant) m = __fmul_rn(m, qc.deq_o);
+    for (int i = 0; i < cnt; i++) out[(size_t)empty_rows[i] * P + j] = m;
+}
+
+}  // namespace sgrace

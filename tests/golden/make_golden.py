@@ -1,0 +1,230 @@
+"""Generates the committed golden fixtures from the reference checkout (/root/reference).
+
+Run in the build container only (the GPU box has no reference checkout):
+    python tests/golden/make_golden.py
+
+Writes into tests/golden/:
+  citeseer_half.npz   Citeseer inputs of the reference (data/matrices/citeseer_*.txt) rounded to
+                      binary16 exactly as main_float.cpp / mmult-master.ipynb load them, plus the
+                      reference's recorded outputs:
+                        csim_rows / csim_vals   hls/.../csim/report/mmult_top_csim.log:21-62
+                        nb37_row0               jupyter/test/mmult-master.ipynb cell 37 output
+                        nb55_row0               jupyter/test/mmult-master.ipynb cell 55 output
+  toy.npz             the 4x4 hand-checkable fixtures test_*.txt (main_float.cpp:102-111)
+  qlayer_*.npz        inputs + outputs of the reference's OWN emulation branch
+                      (demo/sgrace_lib/sgrace.py:563-681) executed here: sgrace.py is imported
+                      unmodified with tiny stand-ins for its unavailable imports
+                      (torch_geometric, torch_scatter) and the reference's emulation config.py.
+  sym_norm2.npz       inputs + outputs of the reference's sym_norm2 (sgrace.py:18-51)
+  ref_hls_*.npz       outputs of the reference HLS source compiled natively (oracle/_ref) on
+                      small seeded inputs, so the GPU box can check against the real kernel code
+"""
+import os
+import re
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+MAT = REF + "/gnn-rfsoc-mt-all-2022/data/matrices/"
+
+from oracle import oracle as O  # noqa: E402
+
+
+def citeseer():
+    adj = O.load_csr_txt(MAT + "citeseer_adj.txt")
+    fea = O.load_csr_txt(MAT + "citeseer_feat.txt")
+    w = O.load_dense_txt(MAT + "citeseer_weights.txt")
+    log = open(REF + "/gnn-rfsoc-mt-all-2022/hls/gnn/solution1/gnn/solution1/csim/report/mmult_top_csim.log").read()
+    rows, cols, vals = [], [], []
+    for m in re.finditer(r"out :data index= (\d+) (\d+) kernel = (\S+)", log):
+        rows.append(int(m.group(1)))
+        cols.append(int(m.group(2)))
+        vals.append(float(m.group(3)))
+    assert len(vals) == 42
+    import json
+    nb = json.load(open(REF + "/jupyter/test/mmult-master.ipynb"))
+    out37 = "".join(nb["cells"][37]["outputs"][0]["text"])
+    out55 = "".join(nb["cells"][55]["outputs"][0]["text"])
+    nb37 = np.array(re.findall(r"-?\d+\.\d+(?:e-?\d+)?", out37), dtype=np.float64)
+    nb55 = np.array(re.findall(r"-?\d+\.\d+(?:e-?\d+)?", out55), dtype=np.float64)
+    assert len(nb37) == 16 and len(nb55) == 21
+    assert np.all(fea.val == 1.0)
+    np.savez_compressed(
+        os.path.join(HERE, "citeseer_half.npz"),
+        adj_rowptr=adj.rowptr, adj_col=adj.col.astype(np.uint16), adj_val_f16=adj.val.astype(np.float16),
+        fea_rowptr=fea.rowptr, fea_col=fea.col.astype(np.uint16),   # all feature values are 1.0
+        w_f16=w.astype(np.float16),
+        csim_rows=np.array(rows, np.int32), csim_cols=np.array(cols, np.int32),
+        csim_vals=np.array(vals, np.float64), nb37_row0=nb37, nb55_row0=nb55)
+    print("citeseer_half.npz", adj.n, adj.nnz, fea.nnz, w.shape)
+
+
+def toy():
+    d = {}
+    for name in ("test_adj", "test_adj2", "test_feat", "test_feat2"):
+        c = O.load_csr_txt(MAT + name + ".txt")
+        d[name + "_rowptr"], d[name + "_col"], d[name + "_val"] = c.rowptr, c.col, c.val
+    for name in ("test_weights", "test_weights2"):
+        d[name] = O.load_dense_txt(MAT + name + ".txt")
+    np.savez_compressed(os.path.join(HERE, "toy.npz"), **d)
+    print("toy.npz")
+
+
+# ---------------------------------------------------------------------------------------
+# import the reference's sgrace.py unmodified
+# ---------------------------------------------------------------------------------------
+def import_reference_sgrace(w_qbits, compute_attention):
+    def degree(index, num_nodes=None, dtype=None):
+        n = int(index.max()) + 1 if num_nodes is None else num_nodes
+        out = torch.zeros(n, dtype=dtype or torch.get_default_dtype())
+        return out.scatter_add_(0, index, torch.ones(index.numel(), dtype=out.dtype))
+
+    def add_remaining_self_loops(edge_index, edge_attr=None, fill_value=None, num_nodes=None):
+        n = num_nodes
+        mask = edge_index[0] != edge_index[1]
+        loop_index = torch.arange(0, n, dtype=edge_index.dtype).unsqueeze(0).repeat(2, 1)
+        loop_attr = None
+        if edge_attr is not None:
+            loop_attr = edge_attr.new_full((n,), fill_value)
+            inv = ~mask
+            loop_attr[edge_index[0][inv]] = edge_attr[inv]      # keep existing self-loop weights
+            edge_attr = torch.cat([edge_attr[mask], loop_attr], dim=0)
+        edge_index = torch.cat([edge_index[:, mask], loop_index], dim=1)
+        return edge_index, edge_attr
+
+    def add_self_loops(edge_index, edge_attr=None, fill_value=None, num_nodes=None):
+        n = num_nodes
+        loop_index = torch.arange(0, n, dtype=edge_index.dtype).unsqueeze(0).repeat(2, 1)
+        if edge_attr is not None:
+            edge_attr = torch.cat([edge_attr, edge_attr.new_full((n,), fill_value)], dim=0)
+        return torch.cat([edge_index, loop_index], dim=1), edge_attr
+
+    def sort_edge_index(edge_index, edge_attr=None, num_nodes=None):
+        n = int(edge_index.max()) + 1
+        key = edge_index[0] * n + edge_index[1]
+        perm = torch.argsort(key, stable=True)
+        return edge_index[:, perm], (None if edge_attr is None else edge_attr[perm])
+
+    def scatter_add(src, index, dim=0, dim_size=None):
+        out = torch.zeros(dim_size, dtype=src.dtype)
+        return out.scatter_add_(0, index, src)
+
+    tg = types.ModuleType("torch_geometric")
+    tg.transforms = types.ModuleType("torch_geometric.transforms")
+    tg.utils = types.ModuleType("torch_geometric.utils")
+    tg.utils.add_remaining_self_loops = add_remaining_self_loops
+    tg.utils.add_self_loops = add_self_loops
+    tg.utils.sort_edge_index = sort_edge_index
+    tg.utils.degree = degree
+    ts = types.ModuleType("torch_scatter")
+    ts.scatter_add = scatter_add
+    sys.modules.update({"torch_geometric": tg, "torch_geometric.transforms": tg.transforms,
+                        "torch_geometric.utils": tg.utils, "torch_scatter": ts})
+    for m in ("config", "sgrace"):
+        sys.modules.pop(m, None)
+    sys.path.insert(0, REF + "/demo/emulation")
+    sys.path.insert(0, REF + "/demo/sgrace_lib")
+    import config
+    config.acc = 0
+    config.accb = 0
+    config.fake_quantization = 1
+    config.w_qbits = w_qbits
+    config.compute_attention = compute_attention
+    config.profiling = 0
+    config.show_max_min = 0
+    import sgrace
+    sgrace.init_SGRACE()
+    sys.path.pop(0)
+    sys.path.pop(0)
+    return config, sgrace
+
+
+def small_graph(rng, n, m, p, dens_x=0.2, extra_edges=3):
+    rows = np.concatenate([np.arange(n)] * extra_edges)
+    cols = rng.integers(0, n, size=len(rows))
+    r = np.concatenate([rows, cols])
+    c = np.concatenate([cols, rows])
+    keep = r != c
+    ei = np.unique(np.stack([r[keep], c[keep]]), axis=1)
+    x = (rng.random((n, m)) < dens_x) * rng.random((n, m))
+    x[rng.integers(0, n, 3)] = 0.0          # a few all-zero feature rows
+    w = rng.uniform(-1.2, 1.2, size=(m, p)) * (rng.random((m, p)) < 0.9)   # some clipping, some zeros
+    att = rng.uniform(-1.0, 1.0, size=(2 * p, 1))
+    return ei.astype(np.int64), x.astype(np.float32), w.astype(np.float32), att.astype(np.float32)
+
+
+def qlayers():
+    rng = np.random.default_rng(7)
+    ei, x, w, att = small_graph(rng, 96, 40, 16)
+    n = x.shape[0]
+    for qbits in (8, 4, 2, 1):
+        for gat in (0, 1):
+            config, sg = import_reference_sgrace(qbits, gat)
+            # the model's own preprocessing: sym_norm2 (sgrace.py:18-51, demo_sgrace.py:233-267)
+            edge_index, norm = sg.sym_norm2(torch.from_numpy(ei), n, None, 1, torch.float32)
+            adj = torch.sparse_coo_tensor(edge_index, norm, (n, n))
+            layer = sg.GATConv_SGRACE(x.shape[1], w.shape[1], nheads=1, bias=False)
+            layer.weight.data = torch.from_numpy(w.copy())
+            layer.attention.data = torch.from_numpy(att.copy())
+            outs = {}
+            for relu in (0, 1):
+                for dense in (0, 1):
+                    with torch.no_grad():
+                        out = layer.forward(gat, dense, relu, torch.from_numpy(x.copy()), edge_index, norm, adj)
+                    outs[f"out_relu{relu}_dense{dense}"] = out.numpy().astype(np.float32)
+            consts = {k: float(getattr(sg, k)) for k in ("w_s", "a_s", "f_s", "deq_o")}
+            consts.update({k: int(getattr(sg, k)) for k in ("w_z", "a_z", "f_z", "scale_fea", "internal_quantization")})
+            np.savez_compressed(
+                os.path.join(HERE, f"qlayer_q{qbits}_gat{gat}.npz"),
+                edge_index=edge_index.numpy().astype(np.int32), norm=norm.numpy().astype(np.float32),
+                x=x, w=w, attention=att, qbits=qbits, gat=gat,
+                **{"c_" + k: np.array(v) for k, v in consts.items()}, **outs)
+            print(f"qlayer_q{qbits}_gat{gat}.npz", consts, {k: float(np.abs(v).max()) for k, v in outs.items()})
+    # sym_norm2 fixture (pre-processing, "next" row)
+    config, sg = import_reference_sgrace(8, 0)
+    e2, n2 = sg.sym_norm2(torch.from_numpy(ei), n, None, 1, torch.float32)
+    np.savez_compressed(os.path.join(HERE, "sym_norm2.npz"), edge_index_in=ei.astype(np.int32), num_nodes=n,
+                        fill=1, edge_index_out=e2.numpy().astype(np.int32), norm_out=n2.numpy().astype(np.float32))
+    print("sym_norm2.npz", e2.shape)
+
+
+def ref_hls():
+    """Outputs of the reference HLS kernel source (compiled in oracle/_ref) on seeded inputs."""
+    if not (O.ref_available("half") and O.ref_available("float")):
+        print("oracle/_ref not built; run `make -C oracle ref` first")
+        return
+    from sgracex1_b200 import graphs as G
+    rng = np.random.default_rng(11)
+    p = G.cora_shape(seed=3, P=16, n=600, m=300, nnz_adj=3000, nnz_fea=6000)
+    p.fea_val = rng.uniform(0.0, 1.0, size=len(p.fea_val)).astype(np.float32)
+    xd = (rng.random((p.N, 24)) < 0.5) * rng.uniform(-1, 1, size=(p.N, 24))
+    wd = rng.uniform(-0.5, 0.5, size=(24, 10)).astype(np.float32)
+    d = dict(N=p.N, M=p.M, adj_rowptr=p.adj_rowptr, adj_col=p.adj_col, adj_val=p.adj_val,
+             fea_rowptr=p.fea_rowptr, fea_col=p.fea_col, fea_val=p.fea_val, W=p.W, x_dense=xd.astype(np.float32),
+             w_dense=wd)
+    for kind, dt in (("half", O.F16), ("float", O.F32)):
+        adj = (p.adj_rowptr, p.adj_col, O.to_storage(p.adj_val, dt))
+        fea = (p.fea_rowptr, p.fea_col, O.to_storage(p.fea_val, dt))
+        for P in (16, 7):
+            for relu in (0, 1):
+                B = O.to_storage(O.weights_to_B(p.W[:, :P]), dt)
+                d[f"{kind}_sparse_P{P}_relu{relu}"] = O.ref_layer(kind=kind, N=p.N, M_fea=p.M, P=P, adj=adj, B=B,
+                                                                  fea=fea, relu=relu)
+        Bd = O.to_storage(O.weights_to_B(wd), dt)
+        d[f"{kind}_dense_P10_relu1"] = O.ref_layer(kind=kind, N=p.N, M_fea=24, P=10, adj=adj, B=Bd,
+                                                   x_dense=O.to_storage(xd, dt), relu=1)
+    np.savez_compressed(os.path.join(HERE, "ref_hls.npz"), **d)
+    print("ref_hls.npz", sorted(k for k in d if "relu" in k))
+
+
+if __name__ == "__main__":
+    citeseer()
+    toy()
+    ref_hls()
+    qlayers()

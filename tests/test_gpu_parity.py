@@ -1,0 +1,318 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle and the
+committed golden fixtures.  Bar: bit-exact for the C-simulation modes (HALF / FLOAT-order /
+ap_fixed) and for the integer stages of the quantised design; 1e-5 relative for float."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from sgracex1_b200 import _lib, quant as Q
+from sgracex1_b200 import graphs as G
+from tests import util as U
+
+pytestmark = pytest.mark.gpu
+
+MODE_OF = {O.F32: _lib.MODE_F32_CSIM, O.F16: _lib.MODE_F16_CSIM, O.FIX16: _lib.MODE_FIX16_CSIM}
+
+
+@pytest.fixture(scope="module")
+def ip():
+    from sgracex1_b200.pynq_compat import MmultTop
+    return MmultTop(0)
+
+
+def run_host(ip, mode, *, N, M, P, adj, B, fea=None, x_dense=None, relu=0, coo=False, **opts):
+    """Through the register map with host buffers (the PYNQ protocol)."""
+    from sgracex1_b200.driver import HostLayer
+    ip.configure(spmm_block=opts.get("spmm_block", 1), lat_fea=opts.get("lat_fea", 0), lat_adj=opts.get("lat_adj", 0),
+                 fea_threads=opts.get("fea_threads", 1), adj_threads=opts.get("adj_threads", 1),
+                 use_sblocks=opts.get("use_sblocks", 0), staging=1, long_row=opts.get("long_row", 512))
+    hl = HostLayer(ip, mode, N=N, M=M, P=P, nnz_adj=len(adj[1]), nnz_fea=(len(fea[1]) if fea is not None else 0),
+                   dense=x_dense is not None, coo=coo)
+    try:
+        hl.load(N=N, M=M, P=P, adj=adj, B=B, fea=fea, x_dense=x_dense, relu=relu)
+        return hl.run()
+    finally:
+        hl.free()
+
+
+# ------------------------------------------------------------------------------------------
+# golden vectors of the reference, straight on the GPU
+# ------------------------------------------------------------------------------------------
+def test_gpu_half_matches_csim_log_and_notebook(ip):
+    g, n, adj, fea, w16 = U.citeseer_half()
+    B21 = np.ascontiguousarray(w16[:, :21].T).view(np.uint16).reshape(-1)
+    D = run_host(ip, _lib.MODE_F16_CSIM, N=n, M=w16.shape[0], P=21, adj=adj, fea=fea, B=B21, spmm_block=4,
+                 lat_fea=4, lat_adj=4).view(np.float16)
+    want = g["csim_vals"].astype(np.float32).astype(np.float16)
+    assert np.array_equal(D[g["csim_rows"], g["csim_cols"]].view(np.uint16), want.view(np.uint16))
+    B16 = np.ascontiguousarray(w16[:, :16].T).view(np.uint16).reshape(-1)
+    D = run_host(ip, _lib.MODE_F16_CSIM, N=n, M=w16.shape[0], P=16, adj=adj, fea=fea, B=B16, spmm_block=1).view(np.float16)
+    want = g["nb37_row0"].astype(np.float32).astype(np.float16)
+    assert np.array_equal(D[0].view(np.uint16), want.view(np.uint16))
+    # whole matrix against the oracle
+    ref = O.layer(dtype=O.F16, N=n, M_fea=w16.shape[0], P=16, adj=adj, fea=fea, B=B16, spmm_block=1)
+    assert np.array_equal(D.view(np.uint16), ref)
+
+
+def test_gpu_float_matches_notebook_scipy_row(ip):
+    g, n, adj, fea, w16 = U.citeseer_half()
+    a = (adj[0], adj[1], adj[2].view(np.float16).astype(np.float32))
+    f = (fea[0], fea[1], np.ones(len(fea[1]), np.float32))
+    B = O.weights_to_B(w16.astype(np.float32))
+    D = run_host(ip, _lib.MODE_F32_FAST, N=n, M=w16.shape[0], P=21, adj=a, fea=f, B=B)
+    np.testing.assert_allclose(D[0], g["nb55_row0"], rtol=1e-5)
+    ref = O.layer(dtype=O.F32, N=n, M_fea=w16.shape[0], P=21, adj=a, fea=f, B=B)
+    U.assert_close_f32(D, ref, what="citeseer float P=21")
+
+
+def test_gpu_matches_compiled_reference_fixtures(ip):
+    g = np.load(os.path.join(U.GOLDEN, "ref_hls.npz"))
+    N, M = int(g["N"]), int(g["M"])
+    for kind, dt in (("half", O.F16), ("float", O.F32)):
+        adj = (g["adj_rowptr"], g["adj_col"], O.to_storage(g["adj_val"], dt))
+        fea = (g["fea_rowptr"], g["fea_col"], O.to_storage(g["fea_val"], dt))
+        for P in (16, 7):
+            for relu in (0, 1):
+                B = O.to_storage(O.weights_to_B(g["W"][:, :P]), dt)
+                D = run_host(ip, MODE_OF[dt], N=N, M=M, P=P, adj=adj, fea=fea, B=B, relu=relu, lat_fea=4, lat_adj=4)
+                assert np.array_equal(D.view(np.uint8), g[f"{kind}_sparse_P{P}_relu{relu}"].view(np.uint8)), (kind, P, relu)
+        Bd = O.to_storage(O.weights_to_B(g["w_dense"]), dt)
+        D = run_host(ip, MODE_OF[dt], N=N, M=24, P=10, adj=adj, x_dense=O.to_storage(g["x_dense"], dt), B=Bd, relu=1,
+                     lat_fea=4, lat_adj=4)
+        assert np.array_equal(D.view(np.uint8), g[f"{kind}_dense_P10_relu1"].view(np.uint8)), kind
+
+
+# ------------------------------------------------------------------------------------------
+# C-simulation modes: bit-exact against the oracle over the knob space
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [O.F32, O.F16, O.FIX16])
+@pytest.mark.parametrize("knobs", [
+    dict(spmm_block=1), dict(spmm_block=4, lat_fea=4, lat_adj=4), dict(spmm_block=8, lat_fea=6, lat_adj=2),
+    dict(spmm_block=2, fea_threads=2, adj_threads=4), dict(spmm_block=4, fea_threads=4, adj_threads=2, lat_fea=3),
+])
+def test_csim_modes_bit_exact(ip, dtype, knobs):
+    for seed, (n, m, p) in enumerate([(203, 64, 16), (97, 33, 21), (64, 7, 5)]):
+        pr = U.random_problem(seed, n=n, m=m, p=p, val_scale=0.3 if dtype == O.FIX16 else 0.5)
+        adj, fea, B, xd = U.to_storage_problem(pr, dtype)
+        for relu in (0, 1):
+            for dense in (False, True):
+                kw = dict(x_dense=xd) if dense else dict(fea=fea)
+                ref = O.layer(dtype=dtype, N=n, M_fea=m, P=p, adj=adj, B=B, relu=relu, **kw, **knobs)
+                got = run_host(ip, MODE_OF[dtype], N=n, M=m, P=p, adj=adj, B=B, relu=relu, **kw, **knobs)
+                assert np.array_equal(got.view(np.uint8), ref.view(np.uint8)), (dtype, knobs, n, m, p, relu, dense)
+
+
+def test_use_sblocks_drops_relu(ip):
+    pr = U.random_problem(9, n=80, m=20, p=8)
+    adj, fea, B, _ = U.to_storage_problem(pr, O.F16)
+    ref = O.layer(dtype=O.F16, N=80, M_fea=20, P=8, adj=adj, fea=fea, B=B, relu=1, use_sblocks=1)
+    got = run_host(ip, _lib.MODE_F16_CSIM, N=80, M=20, P=8, adj=adj, fea=fea, B=B, relu=1, use_sblocks=1)
+    assert np.array_equal(got, ref)
+
+
+# ------------------------------------------------------------------------------------------
+# fast float32 path: 1e-5 relative against the FLOAT-build oracle
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("P", [4, 8, 16, 20, 21, 32, 64, 100, 128, 256])
+def test_fast_float_widths(ip, P):
+    pr = U.random_problem(P, n=301, m=40, p=P)
+    adj, fea, B, xd = U.to_storage_problem(pr, O.F32)
+    for relu in (0, 1):
+        ref = O.layer(dtype=O.F32, N=301, M_fea=40, P=P, adj=adj, fea=fea, B=B, relu=relu)
+        got = run_host(ip, _lib.MODE_F32_FAST, N=301, M=40, P=P, adj=adj, fea=fea, B=B, relu=relu)
+        if relu:   # an element within rounding of zero may flip sign; compare where the oracle is clearly positive
+            assert ((got == 0) | (got > 0)).all()
+        U.assert_close_f32(got, ref, what=f"sparse P={P} relu={relu}")
+        ref = O.layer(dtype=O.F32, N=301, M_fea=40, P=P, adj=adj, x_dense=xd, B=B, relu=relu)
+        got = run_host(ip, _lib.MODE_F32_FAST, N=301, M=40, P=P, adj=adj, x_dense=xd, B=B, relu=relu)
+        U.assert_close_f32(got, ref, what=f"dense P={P} relu={relu}")
+
+
+def test_fast_float_long_rows_and_coo(ip):
+    pr = U.random_problem(21, n=1500, m=30, p=16, avg_deg=3)
+    rp, ci, av = pr["adj"]
+    # make three rows very long (power-law hubs) so the CTA-per-row kernel runs
+    rng = np.random.default_rng(0)
+    deg = np.diff(rp).copy()
+    rows = [np.sort(rng.choice(1500, size=d, replace=False)) for d in deg]
+    for r in (5, 700, 1499):
+        rows[r] = np.arange(1500)[:: 1 if r != 700 else 2]
+    deg = np.array([len(x) for x in rows])
+    rp = np.zeros(1501, np.int32)
+    np.cumsum(deg, out=rp[1:])
+    ci = np.concatenate(rows).astype(np.int32)
+    av = rng.uniform(-0.1, 0.1, size=len(ci)).astype(np.float32)
+    adj = (rp, ci, av)
+    _, fea, B, _ = U.to_storage_problem(pr, O.F32)
+    ref = O.layer(dtype=O.F32, N=1500, M_fea=30, P=16, adj=adj, fea=fea, B=B, relu=1)
+    for coo in (False, True):
+        for long_row in (64, 100000):
+            got = run_host(ip, _lib.MODE_F32_FAST, N=1500, M=30, P=16, adj=adj, fea=fea, B=B, relu=1, coo=coo,
+                           long_row=long_row)
+            U.assert_close_f32(got, ref, what=f"long rows coo={coo} long_row={long_row}")
+
+
+def test_edge_cases(ip):
+    # N=1, empty adjacency, empty features, all-empty rows
+    one = (np.array([0, 1], np.int32), np.array([0], np.int32), np.array([2.0], np.float32))
+    D = run_host(ip, _lib.MODE_F32_FAST, N=1, M=1, P=4, adj=one, fea=one, B=np.array([1, 2, 3, 4], np.float32))
+    assert np.array_equal(D, np.array([[4, 8, 12, 16]], np.float32))
+    empty = (np.zeros(6, np.int32), np.zeros(0, np.int32), np.zeros(0, np.float32))
+    pr = U.random_problem(1, n=5, m=3, p=4)
+    _, fea, B, _ = U.to_storage_problem(pr, O.F32)
+    for mode in (_lib.MODE_F32_FAST, _lib.MODE_F32_CSIM):
+        D = run_host(ip, mode, N=5, M=3, P=4, adj=empty, fea=fea, B=B)
+        assert np.array_equal(D, np.zeros((5, 4), np.float32))
+        D = run_host(ip, mode, N=5, M=3, P=4, adj=pr["adj"], fea=empty, B=B)
+        assert np.array_equal(D, np.zeros((5, 4), np.float32))
+
+
+def test_cora_shape_and_block_diagonal_batch(ip):
+    p = G.cora_shape(seed=0)
+    ref = O.layer(dtype=O.F32, N=p.N, M_fea=p.M, P=p.P, adj=(p.adj_rowptr, p.adj_col, p.adj_val),
+                  fea=(p.fea_rowptr, p.fea_col, p.fea_val), B=p.B, relu=1)
+    got = run_host(ip, _lib.MODE_F32_FAST, N=p.N, M=p.M, P=p.P, adj=(p.adj_rowptr, p.adj_col, p.adj_val),
+                   fea=(p.fea_rowptr, p.fea_col, p.fea_val), B=p.B, relu=1)
+    U.assert_close_f32(got, ref, what="cora shape")
+    # block-diagonal batch: every replica must equal the single-graph result (linearity of the path)
+    b = G.block_diagonal([p], 8)
+    got = run_host(ip, _lib.MODE_F32_FAST, N=b.N, M=b.M, P=b.P, adj=(b.adj_rowptr, b.adj_col, b.adj_val),
+                   fea=(b.fea_rowptr, b.fea_col, b.fea_val), B=b.B, relu=1)
+    for k in range(8):
+        assert np.array_equal(got[k * p.N:(k + 1) * p.N], got[:p.N])
+    U.assert_close_f32(got[:p.N], ref, what="cora batch")
+
+
+def test_device_resident_path_equals_host_path(ip):
+    from sgracex1_b200.driver import DeviceLayer
+    pr = U.random_problem(33, n=400, m=50, p=16)
+    adj, fea, B, _ = U.to_storage_problem(pr, O.F32)
+    host = run_host(ip, _lib.MODE_F32_FAST, N=400, M=50, P=16, adj=adj, fea=fea, B=B, relu=1)
+    dl = DeviceLayer(ip.handle, _lib.MODE_F32_FAST)
+    dl.load(N=400, M=50, P=16, adj=adj, fea=fea, B=B, relu=1)
+    dl.run()
+    assert np.array_equal(dl.result("D"), host)
+    xw = dl.result("XW")
+    ref_d, ref_xw = O.layer(dtype=O.F32, N=400, M_fea=50, P=16, adj=adj, fea=fea, B=B, relu=1, return_xw=True)
+    U.assert_close_f32(xw, ref_xw, what="XW (FEA stage)")
+
+
+# ------------------------------------------------------------------------------------------
+# full design: quantised GCN bit-exact vs oracle, GAT 1e-5; and against the reference emulation
+# ------------------------------------------------------------------------------------------
+def run_full(ip, *, qbits, gat, N, M, P, adj, B, fea=None, x_dense=None, attention=None, relu=0, coo=True):
+    from sgracex1_b200.driver import HostLayer
+    c = Q.layer_constants(qbits) if qbits else None
+    ip.configure(qbits=qbits, staging=1)
+    hl = HostLayer(ip, _lib.MODE_FULL, N=N, M=M, P=P, nnz_adj=len(adj[1]), nnz_fea=(len(fea[1]) if fea is not None else 0),
+                   dense=x_dense is not None, gat=True, coo=coo)
+    try:
+        rm = ip.register_map
+        if c:
+            rm.scale_fea = c["scale_fea"]
+            rm.deq_factor = Q.float_bits(c["deq_o"])
+            rm.quantization_scale_fea = Q.float_bits(1 / c["f_s"])
+            rm.quantization_scale_w = Q.float_bits(1 / c["w_s"])
+            rm.quantization_scale_adj = Q.float_bits(1 / c["a_s"])
+            rm.quantized_multiplier = c["internal_quantization"]
+        hl.load(N=N, M=M, P=P, adj=adj, B=B, fea=fea, x_dense=x_dense, relu=relu, attention=attention, gat_mode=gat)
+        D = hl.run()
+        nnz = len(adj[1])
+        return D, np.array(hl.E[:nnz]), np.array(hl.S[:nnz]), int(rm.max_fea)
+    finally:
+        hl.free()
+
+
+@pytest.mark.parametrize("qbits", [8, 4, 2, 1])
+def test_quantised_gcn_bit_exact_and_reference_emulation(ip, qbits):
+    g = np.load(os.path.join(U.GOLDEN, f"qlayer_q{qbits}_gat0.npz"))
+    x, w = g["x"], g["w"]
+    n, m = x.shape
+    p = w.shape[1]
+    adj = U.coo_to_csr(g["edge_index"], g["norm"], n)
+    consts = Q.layer_constants(qbits)
+    for relu in (0, 1):
+        for dense in (0, 1):
+            kw = dict(x_dense=x) if dense else dict(fea=U.dense_to_csr(x))
+            ref = O.qlayer(N=n, M_fea=m, P=p, adj=adj, B=O.weights_to_B(w), relu=relu, gat=0, qbits=qbits,
+                           consts=consts, return_all=True, **kw)
+            D, _, _, max_fea = run_full(ip, qbits=qbits, gat=0, N=n, M=m, P=p, adj=adj, B=O.weights_to_B(w), relu=relu, **kw)
+            assert np.array_equal(D, ref["D"]), (qbits, relu, dense)
+            assert max_fea == ref["max_fea"]
+            emu = g[f"out_relu{relu}_dense{dense}"]
+            assert np.abs(D - emu).max() <= 4 * np.finfo(np.float32).eps * np.abs(emu).max()
+
+
+@pytest.mark.parametrize("qbits", [8, 4, 2, 1, 0])
+def test_gat_against_oracle_and_reference_emulation(ip, qbits):
+    g = np.load(os.path.join(U.GOLDEN, f"qlayer_q{qbits or 8}_gat1.npz"))
+    x, w, att = g["x"], g["w"], g["attention"]
+    n, m = x.shape
+    p = w.shape[1]
+    adj = U.coo_to_csr(g["edge_index"], g["norm"], n)
+    consts = Q.layer_constants(qbits) if qbits else None
+    for relu in (0, 1):
+        for dense in (0, 1):
+            kw = dict(x_dense=x) if dense else dict(fea=U.dense_to_csr(x))
+            ref = O.qlayer(N=n, M_fea=m, P=p, adj=adj, B=O.weights_to_B(w), attention=att, relu=relu, gat=1,
+                           qbits=qbits, consts=consts, return_all=True, **kw)
+            D, E, S, _ = run_full(ip, qbits=qbits, gat=1, N=n, M=m, P=p, adj=adj, B=O.weights_to_B(w),
+                                  attention=att, relu=relu, **kw)
+            U.assert_close_f32(D, ref["D"], what=f"GAT D q={qbits}")
+            np.testing.assert_allclose(E, ref["E"], rtol=1e-5, atol=1e-7)
+            np.testing.assert_allclose(S, ref["S"], rtol=1e-5, atol=1e-7)
+            if qbits:
+                U.assert_close_f32(D, g[f"out_relu{relu}_dense{dense}"], what=f"GAT vs reference emulation q={qbits}")
+    # softmax rows sum to one over the surviving edges
+    sums = np.add.reduceat(S, adj[0][:-1])
+    np.testing.assert_allclose(sums, 1.0, rtol=1e-5)
+
+
+def test_gat_pruned_and_empty_rows(ip):
+    n, m, p = 64, 12, 8
+    rng = np.random.default_rng(5)
+    x = rng.random((n, m)).astype(np.float32)
+    w = rng.uniform(-1, 1, (m, p)).astype(np.float32)
+    att = rng.uniform(-1, 1, (2 * p, 1)).astype(np.float32)
+    pr = U.random_problem(2, n=n, m=m, p=p, empty_rows=False)
+    rp, ci, _ = pr["adj"]
+    av = rng.uniform(0.0, 1.0, size=len(ci)).astype(np.float32)
+    av[rng.random(len(ci)) < 0.5] = 0.0005           # half of the edges quantise to zero: pruned
+    for r in (3, 40):                                # two rows lose every edge
+        av[rp[r]:rp[r + 1]] = 0.0005
+    adj = (rp, ci, av)
+    consts = Q.layer_constants(8)
+    ref = O.qlayer(N=n, M_fea=m, P=p, adj=adj, B=O.weights_to_B(w), x_dense=x, attention=att, relu=0, gat=1,
+                   qbits=8, consts=consts, return_all=True)
+    for coo in (True, False):
+        D, E, S, _ = run_full(ip, qbits=8, gat=1, N=n, M=m, P=p, adj=adj, B=O.weights_to_B(w), x_dense=x,
+                              attention=att, relu=0, coo=coo)
+        U.assert_close_f32(D, ref["D"], what="GAT pruned")
+        np.testing.assert_allclose(S, ref["S"], rtol=1e-5, atol=1e-7)
+        assert (S[av < 0.001] == 0).all()
+
+
+def test_errors_are_reported(ip):
+    from sgracex1_b200.driver import HostLayer
+    ip.configure(mode=_lib.MODE_F32_FAST, index_format=0, validate=1)
+    pr = U.random_problem(1, n=10, m=4, p=4)
+    adj, fea, B, _ = U.to_storage_problem(pr, O.F32)
+    hl = HostLayer(ip, _lib.MODE_F32_FAST, N=10, M=4, P=4, nnz_adj=len(adj[1]), nnz_fea=len(fea[1]))
+    try:
+        hl.load(N=10, M=4, P=4, adj=adj, B=B, fea=fea)
+        hl.columnIndex_adj[0] = 99                   # out-of-range column index
+        with pytest.raises(_lib.SgraceError):
+            hl.run()
+        hl.columnIndex_adj[0] = adj[1][0]
+        ip.register_map.gemm_mode = 2                # hardware-backward mode: not part of this path
+        with pytest.raises(_lib.SgraceError):
+            ip.register_map.CTRL.AP_START = 1
+        ip.register_map.gemm_mode = 0
+        ip.register_map.N_adj = 10_000_000           # larger than the allocation
+        with pytest.raises(_lib.SgraceError):
+            ip.register_map.CTRL.AP_START = 1
+    finally:
+        ip.configure(validate=0)
+        hl.free()
