@@ -314,17 +314,20 @@ struct OpsF32 {
     static __device__ __forceinline__ bool gt0(T a) { return a > 0.f; }
 };
 struct OpsF16 {
+    // Xilinx Floating-Point Operator semantics (see oracle/sgrace_oracle.c): operands with a zero
+    // exponent field read as signed zero; the exact result is rounded to nearest-even binary16 and
+    // THEN flushed if it is subnormal (underflow detected after rounding -- PTX's .ftz.f16 flushes
+    // on the pre-rounding value and differs when a result rounds up to 2^-14, so it is not used).
+    // float holds the exact product of two halves and float addition of two halves is innocuous
+    // under double rounding (24 >= 2*11 + 2), so float + __float2half_rn is a correctly rounded op.
     typedef unsigned short T;
     static __device__ __forceinline__ T zero() { return 0; }
-    static __device__ __forceinline__ T mul(T a, T b) {
-        T d; asm("mul.rn.ftz.f16 %0, %1, %2;" : "=h"(d) : "h"(a), "h"(b)); return d;
-    }
-    static __device__ __forceinline__ T add(T a, T b) {
-        T d; asm("add.rn.ftz.f16 %0, %1, %2;" : "=h"(d) : "h"(a), "h"(b)); return d;
-    }
-    static __device__ __forceinline__ bool gt0(T a) {
-        return __half2float(__ushort_as_half(a)) > 0.f;
-    }
+    static __device__ __forceinline__ T ftz(T h) { return (h & 0x7c00u) ? h : (T)(h & 0x8000u); }
+    static __device__ __forceinline__ float f(T h) { return __half2float(__ushort_as_half(ftz(h))); }
+    static __device__ __forceinline__ T h(float x) { return ftz(__half_as_ushort(__float2half_rn(x))); }
+    static __device__ __forceinline__ T mul(T a, T b) { return h(__fmul_rn(f(a), f(b))); }
+    static __device__ __forceinline__ T add(T a, T b) { return h(__fadd_rn(f(a), f(b))); }
+    static __device__ __forceinline__ bool gt0(T a) { return __half2float(__ushort_as_half(a)) > 0.f; }
 };
 struct OpsFix16 {
     typedef short T;
