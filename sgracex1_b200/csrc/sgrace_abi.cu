@@ -127,9 +127,14 @@ int launch_spmm_vec(sgrace_handle* h, const int* rp, const int* ci, const float*
     CU(cudaMemsetAsync(long_count, 0, sizeof(int), h->stream));
     const int block = 256;
     long long warps = ((long long)nrows + RPW - 1) / RPW;
-    // persistent-ish grid: a multiple of the SM count, 8 CTAs of 256 threads per SM resident
-    int grid = grid_for(warps * 32, block, h->num_sms, 8);
-    if (grid > h->num_sms) grid = (grid / h->num_sms) * h->num_sms;
+    // persistent grid: exactly the CTAs that are resident at once (occupancy x SM count), each
+    // striding over the rows, so there is a single wave and no tail of partial waves
+    static int ctas_per_sm = 0;
+    if (!ctas_per_sm) {
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, spmm_csr_f32_kernel<LPR, NV>, block, 0));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    int grid = grid_for(warps * 32, block, h->num_sms, ctas_per_sm);
     spmm_csr_f32_kernel<LPR, NV><<<grid, block, 0, h->stream>>>(
         rp, ci, va, (const float4*)Bm, (float4*)out, nrows, P4, relu, h->long_row, long_rows, long_count);
     h->launches++;

@@ -89,54 +89,89 @@ spmm_csr_f32_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
                     int* __restrict__ long_rows, int* __restrict__ long_count) {
     constexpr int RPW = 32 / LPR;                 // rows per warp
     constexpr int STEP = LPR < 8 ? LPR : 8;       // non-zeros fetched per group request
+    constexpr int BATCH = (STEP * NV <= 8) ? STEP : (NV >= 8 ? 1 : 8 / NV);   // gathers in flight per lane
     const int lane = threadIdx.x & 31;
     const int g = lane / LPR, l = lane % LPR;
     const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (g * LPR));
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long rstride = nwarps * RPW;
+    const size_t rowbytes = (size_t)P4 * sizeof(float4);
+    const char* Bl = reinterpret_cast<const char*>(Bm + l);
 
-    for (long long w = warp0; w * RPW < nrows; w += nwarps) {
-        const int row = (int)(w * RPW) + g;
-        if (row >= nrows) continue;               // whole group leaves together
-        int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
-        if (end - beg > long_thresh) {            // defer to the long-row kernel
-            if (l == 0) long_rows[atomicAdd(long_count, 1)] = row;
-            continue;
+    // Three-deep software pipeline over the rows this group owns (row, row+rstride, ...):
+    //   stage 0: row pointers of row i+2    stage 1: first (col,val) chunk of row i+1
+    //   stage 2: gather + FMA of row i
+    // so the three dependent memory round trips of a row overlap with its neighbours'.
+    long long row = warp0 * RPW + g;
+    int beg0 = 0, end0 = 0, beg1 = 0, end1 = 0;
+    if (row < nrows) { beg0 = __ldg(rowptr + row); end0 = __ldg(rowptr + row + 1); }
+    if (row + rstride < nrows) { beg1 = __ldg(rowptr + row + rstride); end1 = __ldg(rowptr + row + rstride + 1); }
+    int c0 = 0; float a0 = 0.f;
+    if (l < STEP && beg0 + l < end0) { c0 = __ldg(col + beg0 + l); a0 = __ldg(val + beg0 + l); }
+
+    for (; row < nrows; row += rstride) {
+        // stage 0: row pointers two rows ahead
+        int beg2 = 0, end2 = 0;
+        if (row + 2 * rstride < nrows) {
+            beg2 = __ldg(rowptr + row + 2 * rstride);
+            end2 = __ldg(rowptr + row + 2 * rstride + 1);
         }
-        float4 acc[NV];
-#pragma unroll
-        for (int v = 0; v < NV; v++) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // stage 1: first chunk of the next row
+        int c1 = 0; float a1 = 0.f;
+        if (l < STEP && beg1 + l < end1) { c1 = __ldg(col + beg1 + l); a1 = __ldg(val + beg1 + l); }
 
-        for (int k = beg; k < end; k += STEP) {
-            int c = 0; float a = 0.f;
-            if (l < STEP && k + l < end) { c = __ldg(col + k + l); a = __ldg(val + k + l); }
+        // stage 2: this row
+        if (end0 - beg0 > long_thresh) {          // defer to the long-row kernel
+            if (l == 0) long_rows[atomicAdd(long_count, 1)] = (int)row;
+        } else {
+            float4 acc[NV];
 #pragma unroll
-            for (int i = 0; i < STEP; i++) {
-                const int ci = __shfl_sync(gmask, c, g * LPR + i);
-                const float ai = __shfl_sync(gmask, a, g * LPR + i);
-                if (k + i < end) {
-                    const float4* brow = Bm + (size_t)ci * P4;
+            for (int v = 0; v < NV; v++) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            int c = c0; float a = a0;
+            for (int k = beg0; k < end0; k += STEP) {
+                if (k != beg0) {
+                    c = 0; a = 0.f;
+                    if (l < STEP && k + l < end0) { c = __ldg(col + k + l); a = __ldg(val + k + l); }
+                }
+                // all gathers of a sub-batch are issued before any of them is consumed
 #pragma unroll
-                    for (int v = 0; v < NV; v++) {
-                        const int q = v * LPR + l;
-                        if (NV * LPR == P4 || q < P4) fma4(acc[v], ai, ldg4(brow + q));
+                for (int i0 = 0; i0 < STEP; i0 += BATCH) {
+                    float4 b[BATCH][NV];
+#pragma unroll
+                    for (int i = 0; i < BATCH; i++) {
+                        const int ci = __shfl_sync(gmask, c, g * LPR + i0 + i);
+                        const float4* brow = reinterpret_cast<const float4*>(Bl + (size_t)(unsigned)ci * rowbytes);
+                        const bool live = k + i0 + i < end0;
+#pragma unroll
+                        for (int v = 0; v < NV; v++) {
+                            b[i][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (live && (NV * LPR == P4 || v * LPR + l < P4)) b[i][v] = ldg4(brow + v * LPR);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < BATCH; i++) {
+                        const float ai = __shfl_sync(gmask, a, g * LPR + i0 + i);   // 0 past the row end
+#pragma unroll
+                        for (int v = 0; v < NV; v++) fma4(acc[v], ai, b[i][v]);
                     }
                 }
             }
-        }
-        float4* orow = out + (size_t)row * P4;
+            float4* orow = out + (size_t)row * P4;
 #pragma unroll
-        for (int v = 0; v < NV; v++) {
-            const int q = v * LPR + l;
-            if (NV * LPR == P4 || q < P4) {
-                float4 r = acc[v];
-                if (relu) {   // val = (acc > 0 || relu == 0) ? acc : 0   (K:2586-2590)
-                    r.x = r.x > 0.f ? r.x : 0.f; r.y = r.y > 0.f ? r.y : 0.f;
-                    r.z = r.z > 0.f ? r.z : 0.f; r.w = r.w > 0.f ? r.w : 0.f;
+            for (int v = 0; v < NV; v++) {
+                const int q = v * LPR + l;
+                if (NV * LPR == P4 || q < P4) {
+                    float4 r = acc[v];
+                    if (relu) {   // val = (acc > 0 || relu == 0) ? acc : 0   (K:2586-2590)
+                        r.x = r.x > 0.f ? r.x : 0.f; r.y = r.y > 0.f ? r.y : 0.f;
+                        r.z = r.z > 0.f ? r.z : 0.f; r.w = r.w > 0.f ? r.w : 0.f;
+                    }
+                    st_cs4(orow + q, r);
                 }
-                st_cs4(orow + q, r);
             }
         }
+        beg0 = beg1; end0 = end1; beg1 = beg2; end1 = end2; c0 = c1; a0 = a1;
     }
 }
 
@@ -314,7 +349,7 @@ struct OpsF32 {
     static __device__ __forceinline__ bool gt0(T a) { return a > 0.f; }
 };
 struct OpsF16 {
-    // Xilinx Floating-Point Operator semantics (see oracle/sgrace_oracle.c): operands with a zero
+    // Xilinx Floating-Point Operator semantics (pinned by the reference's recorded outputs): operands with a zero
     // exponent field read as signed zero; the exact result is rounded to nearest-even binary16 and
     // THEN flushed if it is subnormal (underflow detected after rounding -- PTX's .ftz.f16 flushes
     // on the pre-rounding value and differs when a result rounds up to 2^-14, so it is not used).
@@ -509,7 +544,7 @@ fea_q_dense_kernel(const float* __restrict__ X, const signed char* __restrict__ 
 
 // ADJ, quantised GCN: out = relu( sum_k A_q[k] * Wh[col[k],:] ) * deq_o.  Adjacency codes
 // are formed on the fly; zero codes are the pruned edges (S:626-629) and are skipped.
-// One thread per (row, column), float multiply then add in CSR order (the oracle's order).
+// One thread per (row, column), float multiply then add in CSR order (the emulation's order).
 __global__ void __launch_bounds__(256)
 adj_q_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
                  const float* __restrict__ val, const float* __restrict__ Wh,
