@@ -79,7 +79,9 @@ enum {
     SGRACE_OPT_LONG_ROW = 11,       /* rows with more non-zeros go to the CTA-per-row kernel */
     SGRACE_OPT_LEAKY_ALPHA_BITS = 12, /* float bits of the GAT LeakyReLU slope (default 0.2) */
     SGRACE_OPT_VALIDATE = 13,       /* 1: check CSR structure on the host mirror at start   */
-    SGRACE_OPT_DENSE_TC = 14        /* 1: allow the tcgen05 path for wide dense FEA (FAST)  */
+    SGRACE_OPT_DENSE_TC = 14,       /* 1: allow the tcgen05 path for wide dense FEA (FAST)  */
+    SGRACE_OPT_STREAM_KERNEL = 15   /* 1 (default): TMA-staged persistent SpMM kernel (FAST);
+                                       0: the row-strided kernel (any pointer alignment)    */
 };
 
 /* ---- register offsets: the AXI-Lite map of gat_all_unsigned.hwh:16153-18563 ---- */

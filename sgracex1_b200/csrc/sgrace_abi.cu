@@ -8,11 +8,13 @@
 #include "../../include/sgrace_b200.h"
 #include "sgrace_kernels.cuh"
 #include "sgrace_gemm_tc.cuh"
+#include "sgrace_spmm_stream.cuh"
 
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -46,10 +48,11 @@ struct sgrace_handle {
     // options
     int mode = SGRACE_MODE_F32_FAST;
     int spmm_block = 1, lat_fea = 0, lat_adj = 0, fea_threads = 1, adj_threads = 1, use_sblocks = 0;
-    int index_format = 0, qbits = 8, staging = 1, long_row = 512, validate = 0, dense_tc = 1;
+    int index_format = 0, qbits = 8, staging = 1, long_row = 512, validate = 0, dense_tc = 1, stream_kernel = 1;
     float leaky_alpha = 0.2f;
     // scratch (grow-only)
-    Scratch wrm, xw, wq, s1, s2, rp_fea, rp_adj, lists, counters;
+    Scratch wrm, wdup, xw, wq, s1, s2, rp_fea, rp_adj, lists, counters;
+    int smem_optin = 0;      // cudaDevAttrMaxSharedMemoryPerBlockOptin
     int* max_fea_dev = nullptr;
     // state
     bool running = false;
@@ -152,6 +155,135 @@ int launch_spmm_vec(sgrace_handle* h, const int* rp, const int* ci, const float*
     return 0;
 }
 
+// ------------------------------------------------------------------------------------
+// streaming (TMA-staged, warp-specialised) float32 SpMM dispatch
+// ------------------------------------------------------------------------------------
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// b_rows > 0: Bm has b_rows rows and is a candidate for shared-memory staging (FEA: W)
+template <int LPR, int NV>
+int launch_spmm_stream(sgrace_handle* h, const int* rp, const int* ci, const float* va, const float* Bm, float* out,
+                       int nrows, int P, int relu, long long nnz_hint, int b_rows, int final_out, int b_total_rows) {
+    const int P4 = P / 4;
+    if (int rc = ensure(h, h->lists, sizeof(int) * (size_t)(nrows > 0 ? nrows : 1))) return rc;
+    if (int rc = ensure(h, h->counters, 64)) return rc;
+    int* long_rows = (int*)h->lists.p;
+    int* long_count = (int*)h->counters.p;
+    int* tile_counter = (int*)h->counters.p + 2;
+    CU(cudaMemsetAsync(long_count, 0, sizeof(int), h->stream));
+    CU(cudaMemsetAsync(tile_counter, 0, sizeof(int), h->stream));
+
+    StreamParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.rowptr = rp; sp.col = ci; sp.val = va; sp.out = (float4*)out;
+    sp.nrows = nrows; sp.P4 = P4; sp.relu = relu;
+    sp.streaming_store = final_out;
+    sp.long_rows = long_rows; sp.long_count = long_count; sp.tile_counter = tile_counter;
+    sp.long_thresh = h->long_row;
+    const bool exact = (P4 == LPR * NV);
+
+    // where Bm rows are gathered from: shared memory when the whole matrix fits beside the stages
+    const size_t budget = (size_t)h->smem_optin;
+    const size_t b_plain = (size_t)b_rows * P * 4;
+    int bsrc = BSRC_GLOBAL;
+    // smem gathers: one CTA per SM split into 4 pipelines of 1 producer + 7 consumer warps with
+    // 1024-non-zero stages; global gathers: 2-3 CTAs per SM of one pipeline each, 2048-non-zero stages
+    int C = 2048, G = 1, S = 3;
+    if (b_rows > 0 && !env_int("SGRACE_STREAM_NOSMEM", 0)) {
+        if (LPR == 4 && NV == 1 && exact && env_int("SGRACE_STREAM_DUP", 0) &&
+            stream_smem_bytes(4, 2, 64, 512, (int)(2 * b_plain)) <= budget) {
+            bsrc = BSRC_SMEM_DUP;
+            C = 512; G = 4; S = 2;
+        } else if (stream_smem_bytes(4, 2, 128, 1024, (int)b_plain) <= budget) {
+            bsrc = BSRC_SMEM;
+            C = 1024; G = 4; S = 3;
+        }
+    }
+    C = env_int("SGRACE_STREAM_C", C) & ~3;
+    G = env_int(bsrc == BSRC_GLOBAL ? "SGRACE_STREAM_G_G" : "SGRACE_STREAM_G_S", G);
+    if (G < 1) G = 1;
+    // stage geometry.  smem gathers: a claimed tile holds ~2.5 stages of non-zeros and is cut into
+    // 32 pieces, so a stage is filled to within one piece (~8%) and one claim feeds several stages.
+    // global gathers: latency-bound, occupancy matters more than stage fill -> small row-pointer
+    // slices (tile ~0.6 stage) so that three CTAs fit an SM.
+    const double avg = (nnz_hint > 0 && nrows > 0) ? (double)nnz_hint / nrows : 8.0;
+    int TR = (int)((bsrc == BSRC_GLOBAL ? 0.6 : 2.5) * C / (avg > 1.0 ? avg : 1.0));
+    TR = (TR / 32) * 32;
+    if (TR < 64) TR = 64;
+    if (TR > (bsrc == BSRC_GLOBAL ? 512 : 1024)) TR = bsrc == BSRC_GLOBAL ? 512 : 1024;
+    TR = env_int("SGRACE_STREAM_TR", TR);
+    sp.tile_rows = TR; sp.stage_nnz = C; sp.groups = G;
+
+    sp.b_bytes = bsrc == BSRC_SMEM_DUP ? (int)(2 * b_plain) : bsrc == BSRC_SMEM ? (int)b_plain : 0;
+    sp.Bm = (const float4*)Bm;
+    if (bsrc == BSRC_SMEM_DUP) {
+        if (int rc = ensure(h, h->wdup, 2 * b_plain)) return rc;
+        const int items = b_rows * 8;
+        make_dup_image_kernel<<<(items + 255) / 256, 256, 0, h->stream>>>((const float4*)Bm, (float4*)h->wdup.p, b_rows);
+        h->launches++;
+        CU(cudaGetLastError());
+        sp.Bm = (const float4*)h->wdup.p;
+    }
+    S = env_int(bsrc == BSRC_GLOBAL ? "SGRACE_STREAM_S_G" : "SGRACE_STREAM_S_S", S);
+    while (S > 2 && stream_smem_bytes(G, S, TR, C, sp.b_bytes) > budget) S--;
+    sp.stages = S;
+    const size_t smem = stream_smem_bytes(G, S, TR, C, sp.b_bytes);
+    if (smem > budget) return fail(h, SGRACE_EUNSUPPORTED, "streaming SpMM needs %zu bytes of shared memory", smem);
+
+    const int static_pct = env_int("SGRACE_STREAM_STATIC", 0);
+    sp.dry_run = env_int("SGRACE_STREAM_DRY", 0);
+    sp.prefetch_rows = (bsrc == BSRC_GLOBAL && env_int("SGRACE_STREAM_PREFETCH", 0)) ? b_total_rows : 0;
+#define STREAM_LAUNCH(BS, MT, MB, EX)                                                                          \
+    do {                                                                                                       \
+        auto kern = spmm_stream_f32_kernel<LPR, NV, BS, MT, MB, EX>;                                           \
+        int threads = env_int(BS == BSRC_GLOBAL ? "SGRACE_STREAM_THREADS_G" : "SGRACE_STREAM_THREADS_S",       \
+                              (BS == BSRC_GLOBAL && MT > 384) ? 384 : MT);                                     \
+        if (threads > MT) threads = MT;                                                                        \
+        threads = (threads / (32 * G)) * (32 * G);                                                             \
+        if (threads < 64 * G) threads = 64 * G;                                                                \
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
+        int per_sm = 1;                                                                                        \
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));                       \
+        if (per_sm < 1) return fail(h, SGRACE_ECUDA, "streaming SpMM does not fit an SM (%zu B smem)", smem);  \
+        const int cap = env_int("SGRACE_STREAM_CTAS", 0);                                                      \
+        if (cap > 0 && per_sm > cap) per_sm = cap;                                                             \
+        const long long tiles = ((long long)nrows + TR - 1) / TR;                                              \
+        long long grid = (long long)h->num_sms * per_sm;                                                       \
+        if (grid > tiles) grid = tiles;                                                                        \
+        sp.static_tiles = (int)(tiles * static_pct / 100 / grid);                                              \
+        kern<<<(int)grid, threads, smem, h->stream>>>(sp);                                                     \
+    } while (0)
+    // register budgets: NV == 1 kernels fit 64 registers -> 1024-thread CTAs (smem gathers) or
+    // several 512-thread CTAs per SM (global gathers, latency-bound: occupancy matters); wide rows
+    // (NV > 1) get 512 x 1 -> 128 registers
+    constexpr int MT_SMEM = NV == 1 ? 1024 : 512;
+    constexpr int MB_GLOB = NV == 1 ? 2 : 1;
+    if (bsrc == BSRC_SMEM_DUP) {
+        if (LPR == 4 && NV == 1) STREAM_LAUNCH(BSRC_SMEM_DUP, 1024, 1, true);
+    } else if (bsrc == BSRC_SMEM) {
+        if (exact) STREAM_LAUNCH(BSRC_SMEM, MT_SMEM, 1, true); else STREAM_LAUNCH(BSRC_SMEM, 512, 1, false);
+    } else {
+        if (exact) STREAM_LAUNCH(BSRC_GLOBAL, 512, MB_GLOB, true); else STREAM_LAUNCH(BSRC_GLOBAL, 512, 1, false);
+    }
+#undef STREAM_LAUNCH
+    h->launches++;
+    CU(cudaGetLastError());
+
+    // rows the streaming kernel deferred: CTA per row, deterministic in-CTA reduction
+    constexpr int NVL = (LPR * NV + 31) / 32 > 0 ? (LPR * NV + 31) / 32 : 1;
+    const size_t lsmem = sizeof(float4) * 8 * (size_t)P4;
+    if (lsmem > 48 * 1024)
+        CU(cudaFuncSetAttribute(spmm_long_rows_f32_kernel<NVL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
+    spmm_long_rows_f32_kernel<NVL><<<h->num_sms * 2, 256, lsmem, h->stream>>>(
+        rp, ci, va, (const float4*)Bm, (float4*)out, P4, relu, long_rows, long_count);
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
 template <int NC>
 int launch_spmm_scalar(sgrace_handle* h, const int* rp, const int* ci, const float* va, const float* Bm,
                        float* out, int nrows, int P, int relu) {
@@ -163,9 +295,27 @@ int launch_spmm_scalar(sgrace_handle* h, const int* rp, const int* ci, const flo
 }
 
 int spmm_f32(sgrace_handle* h, const int* rp, const int* ci, const float* va, const float* Bm, float* out,
-             int nrows, int P, int relu) {
+             int nrows, int P, int relu, long long nnz_hint = 0, int b_rows = 0, int final_out = 0,
+             int b_total_rows = 0) {
     if (nrows <= 0 || P <= 0) return 0;
     const bool aligned = (P % 4 == 0) && (((uintptr_t)Bm & 15) == 0) && (((uintptr_t)out & 15) == 0);
+    // the streaming kernel bulk-copies 16-byte groups of the CSR arrays
+    const bool csr_aligned = ((((uintptr_t)rp) | ((uintptr_t)ci) | ((uintptr_t)va)) & 15) == 0;
+    if (aligned && csr_aligned && h->stream_kernel) {
+        const int P4 = P / 4;
+#define SGRACE_STREAM(L, V) return launch_spmm_stream<L, V>(h, rp, ci, va, Bm, out, nrows, P, relu, nnz_hint, b_rows, final_out, b_total_rows)
+        if (P4 == 1) SGRACE_STREAM(1, 1);
+        if (P4 == 2) SGRACE_STREAM(2, 1);
+        if (P4 <= 4) SGRACE_STREAM(4, 1);
+        if (P4 <= 8) SGRACE_STREAM(8, 1);
+        if (P4 <= 16) SGRACE_STREAM(16, 1);
+        if (P4 <= 32) SGRACE_STREAM(32, 1);
+        if (P4 <= 64) SGRACE_STREAM(32, 2);
+        if (P4 <= 128) SGRACE_STREAM(32, 4);
+        if (P4 <= 256) SGRACE_STREAM(32, 8);
+#undef SGRACE_STREAM
+        return fail(h, SGRACE_EUNSUPPORTED, "P_w=%d > 1024 not supported", P);
+    }
     if (aligned) {
         const int P4 = P / 4;
         if (P4 == 1) return launch_spmm_vec<1, 1>(h, rp, ci, va, Bm, out, nrows, P, relu);
@@ -299,7 +449,7 @@ int run_fea(sgrace_handle* h, const sgrace_layer_desc* d, const int* rp_fea, voi
             if (int rc = transpose_b<float>(h, d->B, h->wrm.p, M, P)) return rc;
             if (d->gemm_mode == 0)
                 return spmm_f32(h, rp_fea, d->columnIndex_fea, (const float*)d->values_fea,
-                                (const float*)h->wrm.p, (float*)XW, N, P, 0);
+                                (const float*)h->wrm.p, (float*)XW, N, P, 0, d->nnz_fea, M, 0);
             if (h->dense_tc && fea_dense_tc_supported(N, M, P)) {
                 int rc = fea_dense_tc_launch((const float*)d->values_fea, (const float*)d->B, (float*)XW, N, M, P,
                                              h->num_sms, h->stream);
@@ -359,7 +509,6 @@ int run_fea(sgrace_handle* h, const sgrace_layer_desc* d, const int* rp_fea, voi
 
 int run_adj(sgrace_handle* h, const sgrace_layer_desc* d, const int* rp_adj, const void* XW, int xw_rows) {
     const int N = d->N_adj, P = d->P_w;
-    (void)xw_rows;
     if (N <= 0 || P <= 0) return 0;
     if (!rp_adj || !d->columnIndex_adj || !d->values_adj || !d->D)
         return fail(h, SGRACE_EINVAL, "adjacency / D pointer not set");
@@ -369,7 +518,7 @@ int run_adj(sgrace_handle* h, const sgrace_layer_desc* d, const int* rp_adj, con
     switch (h->mode) {
         case SGRACE_MODE_F32_FAST:
             return spmm_f32(h, rp_adj, d->columnIndex_adj, (const float*)d->values_adj, (const float*)XW,
-                            (float*)d->D, N, P, relu);
+                            (float*)d->D, N, P, relu, d->nnz_adj, 0, 1, xw_rows);
         case SGRACE_MODE_F32_CSIM:
         case SGRACE_MODE_F16_CSIM:
         case SGRACE_MODE_FIX16_CSIM: {
@@ -589,6 +738,7 @@ int sgrace_create(int device, sgrace_handle** out) {
         return SGRACE_ECUDA;
     }
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     for (int i = 0; i < 5; i++) cudaEventCreate(&h->ev[i]);
     *out = h;
     return SGRACE_OK;
@@ -602,7 +752,7 @@ int sgrace_destroy(sgrace_handle* h) {
         cudaFree(kv.second.dev);
         cudaFreeHost(kv.second.host);
     }
-    Scratch* all[] = {&h->wrm, &h->xw, &h->wq, &h->s1, &h->s2, &h->rp_fea, &h->rp_adj, &h->lists, &h->counters};
+    Scratch* all[] = {&h->wrm, &h->wdup, &h->xw, &h->wq, &h->s1, &h->s2, &h->rp_fea, &h->rp_adj, &h->lists, &h->counters};
     for (Scratch* s : all) if (s->p) cudaFree(s->p);
     if (h->max_fea_dev) cudaFree(h->max_fea_dev);
     for (int i = 0; i < 5; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -713,6 +863,7 @@ int sgrace_set_option(sgrace_handle* h, int key, int64_t v) {
         case SGRACE_OPT_LEAKY_ALPHA_BITS: { uint32_t b = (uint32_t)v; memcpy(&h->leaky_alpha, &b, 4); break; }
         case SGRACE_OPT_VALIDATE: h->validate = v != 0; break;
         case SGRACE_OPT_DENSE_TC: h->dense_tc = v != 0; break;
+        case SGRACE_OPT_STREAM_KERNEL: h->stream_kernel = v != 0; break;
         default: return fail(h, SGRACE_EINVAL, "unknown option %d", key);
     }
     return SGRACE_OK;
@@ -735,6 +886,7 @@ int sgrace_get_option(sgrace_handle* h, int key, int64_t* v) {
         case SGRACE_OPT_LEAKY_ALPHA_BITS: { uint32_t b; memcpy(&b, &h->leaky_alpha, 4); *v = b; break; }
         case SGRACE_OPT_VALIDATE: *v = h->validate; break;
         case SGRACE_OPT_DENSE_TC: *v = h->dense_tc; break;
+        case SGRACE_OPT_STREAM_KERNEL: *v = h->stream_kernel; break;
         default: return fail(h, SGRACE_EINVAL, "unknown option %d", key);
     }
     return SGRACE_OK;
