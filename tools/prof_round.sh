@@ -1,0 +1,8 @@
+# Round profile: (1) plain run, (2) launch list with device times, (3) ncu --set full of the two streaming launches
+set -e
+R=${1:-r1}
+python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/${R}_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -s 15 -c 10 --csv --log-file gpurun_out/${R}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/${R}_ncu1.log 2>&1
+python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/${R}_plain2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:spmm_stream -s 6 -c 2 -f -o gpurun_out/${R}_spmm_stream python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/${R}_ncu2.log 2>&1
+tail -1 gpurun_out/${R}_ncu2.log | cut -c1-100
