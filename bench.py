@@ -343,6 +343,9 @@ def main():
     ap.add_argument("--workload", default="cora_x1024", choices=["cora_x1024", "products", "molecule"])
     ap.add_argument("--copies", type=int, default=1024, help="Cora-shape graphs per step per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--graphs", type=int, default=0, help="molecule workload: graphs per step per GPU (default 188*64)")
+    ap.add_argument("--hidden", type=int, default=0, help="molecule workload: hidden width (default 64)")
+    ap.add_argument("--scale", type=float, default=1.0, help="products workload: fraction of the 2.45M-node shape")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

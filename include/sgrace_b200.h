@@ -144,7 +144,8 @@ int sgrace_reg_offset(const char* name, uint32_t* offset);                 /* "N
 
 int sgrace_set_option(sgrace_handle* h, int key, int64_t value);
 int sgrace_get_option(sgrace_handle* h, int key, int64_t* value);
-int sgrace_set_stream(sgrace_handle* h, void* cuda_stream);                /* NULL: own stream      */
+int sgrace_set_stream(sgrace_handle* h, void* cuda_stream);   /* NULL: the handle's own stream;
+                                                                 (void*)1 = cudaStreamLegacy (the default stream) */
 
 /* ---- run: one layer per start, as one AP_START pulse does ---- */
 int sgrace_start(sgrace_handle* h);

@@ -138,7 +138,12 @@ class Handle:
         return int(v.value)
 
     def set_stream(self, cuda_stream_ptr):
+        """Bind the handle to a CUDA stream (0 / None: the handle's own).  Re-binding synchronises the
+        old stream, so repeated calls with the same stream are skipped."""
+        if getattr(self, "_stream", -1) == (cuda_stream_ptr or 0):
+            return
         self._ck(self.lib.sgrace_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)))
+        self._stream = cuda_stream_ptr or 0
 
     # buffers ---------------------------------------------------------------
     def alloc(self, nbytes):

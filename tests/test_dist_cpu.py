@@ -1,0 +1,148 @@
+"""CPU tests (gloo, world_size 2) of the multi-GPU host logic: the row partition + in-place
+all-gather of XW and the data-parallel gradient all-reduce.  The accelerator calls are replaced by
+torch stand-ins here (the CUDA path is covered by the -m gpu tests); what is checked is that the
+sharded result equals the single-process result."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from sgracex1_b200 import dist as sdist
+from sgracex1_b200 import graphs as G
+from sgracex1_b200 import molecule_gcn as MG
+from tests import util as U
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def torch_fea(x_local, W, out_slot):
+    out_slot.copy_(x_local @ W)
+
+
+def torch_adj(adj_local, xw_full, relu):
+    rp, ci, va = adj_local
+    A = torch.sparse_csr_tensor(rp.long(), ci.long(), va, size=(rp.numel() - 1, xw_full.shape[0]))
+    out = A @ xw_full
+    return out.relu() if relu else out
+
+
+def torch_layer(handle, adj_csr, x, weight, relu):
+    xw = x if weight is None else x @ weight
+    return torch_adj(adj_csr, xw, relu)
+
+
+def _row_partition_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pr = U.random_problem(5, n=203, m=24, p=16)
+    rp, ci, va = pr["adj"]
+    lo, hi = sdist.row_range(203, rank, world)
+    loc = sdist.csr_row_slice(rp, ci, va, lo, hi)
+    adj_local = tuple(torch.from_numpy(np.ascontiguousarray(a)) for a in loc)
+    layer = sdist.RowPartitionedLayer(203, 16, rank, world, "cpu", torch_fea, torch_adj)
+    D = layer.forward(torch.from_numpy(pr["x"][lo:hi]), torch.from_numpy(pr["W"]), adj_local, 1)
+    q.put((rank, lo, hi, D.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_row_partition_equals_single_process():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_row_partition_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    pr = U.random_problem(5, n=203, m=24, p=16)
+    A = np.zeros((203, 203), np.float32)
+    rp, ci, va = pr["adj"]
+    for r in range(203):
+        A[r, ci[rp[r]:rp[r + 1]]] = va[rp[r]:rp[r + 1]]
+    want = np.maximum(A @ (pr["x"] @ pr["W"]), 0)
+    full = np.zeros_like(want)
+    for rank, lo, hi, D in got:
+        assert D.shape == (hi - lo, 16)
+        full[lo:hi] = D
+    np.testing.assert_allclose(full, want, rtol=1e-5, atol=1e-6)
+
+
+def _molecule_setup(n_graphs):
+    prob, batch, y = G.molecule_batch(n_graphs=n_graphs, seed=7, P=16)
+    x = np.zeros((prob.N, prob.M), np.float32)
+    x[np.arange(prob.N), prob.fea_col] = 1.0
+    return prob, batch, y, x
+
+
+def _shard(prob, batch, y, x, g0, g1):
+    nodes = np.nonzero((batch >= g0) & (batch < g1))[0]
+    n0, n1 = int(nodes[0]), int(nodes[-1]) + 1
+    rp, ci, va = sdist.csr_row_slice(prob.adj_rowptr, prob.adj_col, prob.adj_val, n0, n1)
+    return (torch.from_numpy(x[n0:n1]), (torch.from_numpy(rp), torch.from_numpy(ci - n0), torch.from_numpy(va)),
+            torch.from_numpy(batch[n0:n1] - g0), torch.from_numpy(y[g0:g1].astype(np.int64)))
+
+
+def _dp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_graphs = 12
+    prob, batch, y, x = _molecule_setup(n_graphs)
+    g0, g1 = sdist.shard_graphs(n_graphs, rank, world)
+    xs, adj, bs, ys = _shard(prob, batch, y, x, g0, g1)
+    model = MG.GCN_B200(16, None, layer_fn=torch_layer)
+    model.eval()                                   # no dropout: results must match exactly
+    out = model(xs, adj, bs, g1 - g0)
+    loss = torch.nn.CrossEntropyLoss(reduction="sum")(out, ys) / n_graphs
+    loss.backward()
+    sdist.flat_allreduce_grads(model.parameters())
+    q.put((rank, [p.grad.numpy().copy() for p in model.parameters() if p.grad is not None]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gradients_equal_single_process():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dp_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n_graphs = 12
+    prob, batch, y, x = _molecule_setup(n_graphs)
+    xs, adj, bs, ys = _shard(prob, batch, y, x, 0, n_graphs)
+    model = MG.GCN_B200(16, None, layer_fn=torch_layer)
+    model.eval()
+    loss = torch.nn.CrossEntropyLoss(reduction="sum")(model(xs, adj, bs, n_graphs), ys) / n_graphs
+    loss.backward()
+    want = [p.grad.numpy() for p in model.parameters() if p.grad is not None]
+    for r in range(world):
+        assert len(got[r]) == len(want)
+        for a, b in zip(got[r], want):
+            np.testing.assert_allclose(a, b, rtol=2e-5, atol=1e-6)
+
+
+def test_partition_helpers():
+    for n, w in ((10, 3), (2449029, 8), (7, 8), (16, 4)):
+        blocks = [sdist.row_range(n, r, w) for r in range(w)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
+        assert max(hi - lo for lo, hi in blocks) <= sdist.row_block(n, w)
+        shards = [sdist.shard_graphs(n, r, w) for r in range(w)]
+        assert shards[0][0] == 0 and shards[-1][1] == n
+        assert max(b - a for a, b in shards) - min(b - a for a, b in shards) <= 1
