@@ -316,3 +316,36 @@ def test_errors_are_reported(ip):
     finally:
         ip.configure(validate=0)
         hl.free()
+
+
+# ------------------------------------------------------------------------------------------
+# dense FEA on the tensor cores (tcgen05, 3xTF32): 1e-5 against the FLOAT-build oracle
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(1000, 100, 256), (333, 64, 128), (4097, 128, 384), (129, 36, 128)])
+def test_dense_fea_tensor_core_path(ip, shape):
+    from sgracex1_b200.driver import DeviceLayer
+    n, m, p = shape
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((n, m)).astype(np.float32)
+    w = rng.uniform(-0.1, 0.1, size=(m, p)).astype(np.float32)
+    deg = rng.integers(1, 6, size=n)
+    rp = np.zeros(n + 1, np.int32)
+    np.cumsum(deg, out=rp[1:])
+    ci = np.concatenate([np.sort(rng.choice(n, size=d, replace=False)) for d in deg]).astype(np.int32)
+    av = rng.uniform(0.1, 0.5, size=len(ci)).astype(np.float32)
+    adj = (rp, ci, av)
+    ref_d, ref_xw = O.layer(dtype=O.F32, N=n, M_fea=m, P=p, adj=adj, x_dense=x, B=O.weights_to_B(w), relu=1, return_xw=True)
+    ip.configure(staging=0)
+    got = {}
+    for tcore in (1, 0):
+        ip.configure(dense_tc=tcore)
+        dl = DeviceLayer(ip.handle, _lib.MODE_F32_FAST)
+        l0 = ip.handle.launch_count()
+        dl.load(N=n, M=m, P=p, adj=adj, x_dense=x, B=O.weights_to_B(w), relu=1)
+        dl.run()
+        got[tcore] = (dl.result("XW").copy(), dl.result("D").copy())
+        U.assert_close_f32(got[tcore][0], ref_xw, what=f"dense FEA XW tensor_core={tcore} {shape}")
+        U.assert_close_f32(got[tcore][1], ref_d, what=f"dense layer D tensor_core={tcore} {shape}")
+    ip.configure(dense_tc=1, staging=1)
+    # the two paths are different arithmetic (3xTF32 vs FMA) and must agree to float tolerance
+    U.assert_close_f32(got[1][0], got[0][0], rtol=1e-5, what="tensor-core vs CUDA-core XW")
