@@ -908,12 +908,14 @@ int sgrace_set_stream(sgrace_handle* h, void* s) {
 
 int sgrace_layer_run(sgrace_handle* h, const sgrace_layer_desc* d) {
     if (!h) return SGRACE_EINVAL;
+    h->last_status = 0;
     CU(cudaSetDevice(h->device));
     return layer_run_impl(h, d, false);
 }
 
 int sgrace_fea_run(sgrace_handle* h, const sgrace_layer_desc* d, void* XW_out) {
     if (!h) return SGRACE_EINVAL;
+    h->last_status = 0;
     CU(cudaSetDevice(h->device));
     if (int rc = check_desc(h, d)) return rc;
     if (!XW_out) return fail(h, SGRACE_EINVAL, "XW_out is null");
@@ -924,6 +926,7 @@ int sgrace_fea_run(sgrace_handle* h, const sgrace_layer_desc* d, void* XW_out) {
 
 int sgrace_adj_run(sgrace_handle* h, const sgrace_layer_desc* d, const void* XW_in, int32_t xw_rows) {
     if (!h) return SGRACE_EINVAL;
+    h->last_status = 0;
     CU(cudaSetDevice(h->device));
     if (int rc = check_desc(h, d)) return rc;
     if (!XW_in) return fail(h, SGRACE_EINVAL, "XW_in is null");
