@@ -80,8 +80,11 @@ enum {
     SGRACE_OPT_LEAKY_ALPHA_BITS = 12, /* float bits of the GAT LeakyReLU slope (default 0.2) */
     SGRACE_OPT_VALIDATE = 13,       /* 1: check CSR structure on the host mirror at start   */
     SGRACE_OPT_DENSE_TC = 14,       /* 1: allow the tcgen05 path for wide dense FEA (FAST)  */
-    SGRACE_OPT_STREAM_KERNEL = 15   /* 1 (default): TMA-staged persistent SpMM kernel (FAST);
+    SGRACE_OPT_STREAM_KERNEL = 15,  /* 1 (default): TMA-staged persistent SpMM kernel (FAST);
                                        0: the row-strided kernel (any pointer alignment)    */
+    SGRACE_OPT_AGG_FIRST = 16       /* 1: dense layers with M_fea < P_w run as act((A.X).W) --
+                                       equal up to float rounding, gathers narrower rows;
+                                       0 (default): the reference's order act(A.(X.W))      */
 };
 
 /* ---- register offsets: the AXI-Lite map of gat_all_unsigned.hwh:16153-18563 ---- */
@@ -181,6 +184,12 @@ int sgrace_layer_run(sgrace_handle* h, const sgrace_layer_desc* d);        /* as
 /* stages separately, for multi-GPU row partitioning (all-gather of XW between them) */
 int sgrace_fea_run(sgrace_handle* h, const sgrace_layer_desc* d, void* XW_out);
 int sgrace_adj_run(sgrace_handle* h, const sgrace_layer_desc* d, const void* XW_in, int32_t xw_rows);
+
+/* the dense FEA stage on its own with an optional ReLU: out = act(X . W), X dense N x M, B = W
+ * transposed (P x M).  What loop_fea does in gemm_mode 1 (kernelMatrixmult_all.cpp:847-865); used by
+ * multi-GPU callers of the aggregate-first order, where the activation follows the dense stage */
+int sgrace_dense_run(sgrace_handle* h, const void* X, const void* B, void* out, int32_t N, int32_t M, int32_t P,
+                     int32_t relu);
 
 /* number of this library's kernels launched on the handle since creation (bench evidence) */
 int sgrace_launch_count(sgrace_handle* h, uint64_t* count);

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libsgrace_b200.so")
 MODE_F32_FAST, MODE_F32_CSIM, MODE_F16_CSIM, MODE_FIX16_CSIM, MODE_FULL = 0, 1, 2, 3, 4
 (OPT_MODE, OPT_SPMM_BLOCK, OPT_LAT_FEA, OPT_LAT_ADJ, OPT_FEA_THREADS, OPT_ADJ_THREADS,
  OPT_USE_SBLOCKS, OPT_INDEX_FORMAT, OPT_QBITS, OPT_STAGING, OPT_LONG_ROW, OPT_LEAKY_ALPHA_BITS,
- OPT_VALIDATE, OPT_DENSE_TC, OPT_STREAM_KERNEL) = range(1, 16)
+ OPT_VALIDATE, OPT_DENSE_TC, OPT_STREAM_KERNEL, OPT_AGG_FIRST) = range(1, 17)
 REG_CTRL, REG_MAX_FEA = 0x00, 0x70
 
 EXPORTS = (
@@ -23,7 +23,7 @@ EXPORTS = (
     "sgrace_read_reg", "sgrace_write_reg64", "sgrace_reg_offset", "sgrace_set_option",
     "sgrace_get_option", "sgrace_set_stream", "sgrace_start", "sgrace_done", "sgrace_wait",
     "sgrace_stage_times", "sgrace_layer_run", "sgrace_fea_run", "sgrace_adj_run",
-    "sgrace_launch_count",
+    "sgrace_launch_count", "sgrace_dense_run",
 )
 
 
@@ -88,6 +88,7 @@ def load():
     lib.sgrace_fea_run.argtypes = [H, C.POINTER(LayerDesc), C.c_void_p]
     lib.sgrace_adj_run.argtypes = [H, C.POINTER(LayerDesc), C.c_void_p, C.c_int32]
     lib.sgrace_launch_count.argtypes = [H, C.POINTER(C.c_uint64)]
+    lib.sgrace_dense_run.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     for name in EXPORTS:
         if name not in ("sgrace_last_error", "sgrace_version"):
             getattr(lib, name).restype = C.c_int
@@ -197,6 +198,10 @@ class Handle:
 
     def adj_run(self, desc: LayerDesc, xw_in_ptr, xw_rows):
         self._ck(self.lib.sgrace_adj_run(self.h, C.byref(desc), C.c_void_p(xw_in_ptr), int(xw_rows)))
+
+    def dense_run(self, x_ptr, b_ptr, out_ptr, N, M, P, relu=0):
+        self._ck(self.lib.sgrace_dense_run(self.h, C.c_void_p(x_ptr), C.c_void_p(b_ptr), C.c_void_p(out_ptr), int(N), int(M),
+                                           int(P), int(relu)))
 
     def launch_count(self):
         v = C.c_uint64()

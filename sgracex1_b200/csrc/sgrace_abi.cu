@@ -48,10 +48,10 @@ struct sgrace_handle {
     // options
     int mode = SGRACE_MODE_F32_FAST;
     int spmm_block = 1, lat_fea = 0, lat_adj = 0, fea_threads = 1, adj_threads = 1, use_sblocks = 0;
-    int index_format = 0, qbits = 8, staging = 1, long_row = 512, validate = 0, dense_tc = 1, stream_kernel = 1;
+    int index_format = 0, qbits = 8, staging = 1, long_row = 512, validate = 0, dense_tc = 1, stream_kernel = 1, agg_first = 0;
     float leaky_alpha = 0.2f;
     // scratch (grow-only)
-    Scratch wrm, wdup, xw, wq, s1, s2, rp_fea, rp_adj, lists, counters;
+    Scratch wrm, wdup, ax, long_partial, long_done, xw, wq, s1, s2, rp_fea, rp_adj, lists, counters;
     int smem_optin = 0;      // cudaDevAttrMaxSharedMemoryPerBlockOptin
     int* max_fea_dev = nullptr;
     // state
@@ -106,6 +106,11 @@ int default_lat(int mode) {   // matrix_mult.h:117-118,137-138,149-150
     }
 }
 
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
 inline int grid_for(long long work_items, int block, int num_sms, int max_waves = 32) {
     long long g = (work_items + block - 1) / block;
     long long cap = (long long)num_sms * max_waves;
@@ -113,6 +118,42 @@ inline int grid_for(long long work_items, int block, int num_sms, int max_waves 
     if (g < 1) g = 1;
     return (int)g;
 }
+
+// rows the main kernel deferred (longer than the threshold / a stage): segmented CTA-per-segment kernel
+// with deterministic last-arriver combine; the row-per-CTA kernel covers lists it cannot hold
+template <int NVL>
+int launch_long_rows(sgrace_handle* h, const int* rp, const int* ci, const float* va, const float* Bm, float* out, int P4,
+                     int relu, int* long_rows, int* long_count, long long nnz_hint) {
+    const size_t lsmem = sizeof(float4) * 8 * (size_t)P4;
+    // segments <= nnz/SEG + #long rows, #long rows <= nnz/threshold
+    const long long max_rows = nnz_hint > 0 ? nnz_hint / (h->long_row > 0 ? h->long_row : 1) + 1 : 0;
+    const long long max_segs = nnz_hint > 0 ? nnz_hint / LONG_SEG + max_rows + 1 : 0;
+    const size_t part_bytes = (size_t)max_segs * P4 * sizeof(float4);
+    const bool seg = nnz_hint > 0 && part_bytes <= ((size_t)1 << 30) && !env_int("SGRACE_LONG_NOSEG", 0);
+    if (seg) {
+        if (int rc = ensure(h, h->long_partial, part_bytes + 16)) return rc;
+        // per-row completion counters: zeroed once when (re)allocated, reset by the kernel after use
+        const size_t done_bytes = sizeof(int) * (size_t)LONG_LIST_MAX;
+        if (h->long_done.bytes < done_bytes) {
+            if (int rc = ensure(h, h->long_done, done_bytes)) return rc;
+            CU(cudaMemsetAsync(h->long_done.p, 0, h->long_done.bytes, h->stream));
+        }
+        if (lsmem > 12 * 1024)
+            CU(cudaFuncSetAttribute(spmm_long_rows_seg_f32_kernel<NVL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
+        spmm_long_rows_seg_f32_kernel<NVL><<<h->num_sms * 4, 256, lsmem, h->stream>>>(
+            rp, ci, va, (const float4*)Bm, (float4*)out, P4, relu, long_rows, long_count, (float4*)h->long_partial.p,
+            (int*)h->long_done.p);
+    } else {
+        if (lsmem > 48 * 1024)
+            CU(cudaFuncSetAttribute(spmm_long_rows_f32_kernel<NVL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
+        spmm_long_rows_f32_kernel<NVL><<<h->num_sms * 2, 256, lsmem, h->stream>>>(
+            rp, ci, va, (const float4*)Bm, (float4*)out, P4, relu, long_rows, long_count);
+    }
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
 
 // ------------------------------------------------------------------------------------
 // fast float32 SpMM dispatch
@@ -142,26 +183,14 @@ int launch_spmm_vec(sgrace_handle* h, const int* rp, const int* ci, const float*
         rp, ci, va, (const float4*)Bm, (float4*)out, nrows, P4, relu, h->long_row, long_rows, long_count);
     h->launches++;
     CU(cudaGetLastError());
-    // long rows (power-law graphs): CTA per row, deterministic in-CTA reduction
     constexpr int NVL = (LPR * NV + 31) / 32 > 0 ? (LPR * NV + 31) / 32 : 1;
-    size_t smem = sizeof(float4) * 8 * (size_t)P4;
-    if (smem > 48 * 1024)
-        CU(cudaFuncSetAttribute(spmm_long_rows_f32_kernel<NVL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem));
-    spmm_long_rows_f32_kernel<NVL><<<h->num_sms * 2, 256, smem, h->stream>>>(
-        rp, ci, va, (const float4*)Bm, (float4*)out, P4, relu, long_rows, long_count);
-    h->launches++;
-    CU(cudaGetLastError());
+    if (int rc = launch_long_rows<NVL>(h, rp, ci, va, Bm, out, P4, relu, long_rows, long_count, 0)) return rc;
     return 0;
 }
 
 // ------------------------------------------------------------------------------------
 // streaming (TMA-staged, warp-specialised) float32 SpMM dispatch
 // ------------------------------------------------------------------------------------
-int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
-}
 
 // b_rows > 0: Bm has b_rows rows and is a candidate for shared-memory staging (FEA: W)
 template <int LPR, int NV>
@@ -235,6 +264,7 @@ int launch_spmm_stream(sgrace_handle* h, const int* rp, const int* ci, const flo
 
     const int static_pct = env_int("SGRACE_STREAM_STATIC", 0);
     sp.dry_run = env_int("SGRACE_STREAM_DRY", 0);
+    sp.l1_prefetch = bsrc == BSRC_GLOBAL ? env_int("SGRACE_STREAM_PF", 0) : 0;
     sp.prefetch_rows = (bsrc == BSRC_GLOBAL && env_int("SGRACE_STREAM_PREFETCH", 0)) ? b_total_rows : 0;
 #define STREAM_LAUNCH(BS, MT, MB, EX)                                                                          \
     do {                                                                                                       \
@@ -272,15 +302,8 @@ int launch_spmm_stream(sgrace_handle* h, const int* rp, const int* ci, const flo
     h->launches++;
     CU(cudaGetLastError());
 
-    // rows the streaming kernel deferred: CTA per row, deterministic in-CTA reduction
     constexpr int NVL = (LPR * NV + 31) / 32 > 0 ? (LPR * NV + 31) / 32 : 1;
-    const size_t lsmem = sizeof(float4) * 8 * (size_t)P4;
-    if (lsmem > 48 * 1024)
-        CU(cudaFuncSetAttribute(spmm_long_rows_f32_kernel<NVL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
-    spmm_long_rows_f32_kernel<NVL><<<h->num_sms * 2, 256, lsmem, h->stream>>>(
-        rp, ci, va, (const float4*)Bm, (float4*)out, P4, relu, long_rows, long_count);
-    h->launches++;
-    CU(cudaGetLastError());
+    if (int rc = launch_long_rows<NVL>(h, rp, ci, va, Bm, out, P4, relu, long_rows, long_count, nnz_hint)) return rc;
     return 0;
 }
 
@@ -403,6 +426,21 @@ int make_rowptr(sgrace_handle* h, Scratch& s, const int* rows, int nnz, int n, c
     return 0;
 }
 
+// dense X (N x M) times W given as the B buffer (W transposed, P x M): tensor cores when the shape
+// is a real contraction, CUDA cores otherwise.  Needs h->wrm = W row-major for the CUDA-core kernel.
+int dense_f32(sgrace_handle* h, const float* X, const float* B, float* out, int N, int M, int P, int relu) {
+    if (h->dense_tc && fea_dense_tc_supported(N, M, P)) {
+        int rc = fea_dense_tc_launch(X, B, out, N, M, P, h->num_sms, h->stream, 0, relu);
+        if (rc == 0) { h->launches++; return 0; }
+        if (rc != -100) return fail(h, SGRACE_ECUDA, "tcgen05 dense FEA launch failed (%d)", rc);
+    }
+    dim3 grid((N + 63) / 64, (P + 63) / 64);
+    fea_dense_f32_kernel<<<grid, 256, 0, h->stream>>>(X, (const float*)h->wrm.p, out, N, M, P, relu);
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
 QConst make_qconst(const sgrace_handle* h, const sgrace_layer_desc* d) {
     QConst q;
     memset(&q, 0, sizeof(q));
@@ -450,18 +488,7 @@ int run_fea(sgrace_handle* h, const sgrace_layer_desc* d, const int* rp_fea, voi
             if (d->gemm_mode == 0)
                 return spmm_f32(h, rp_fea, d->columnIndex_fea, (const float*)d->values_fea,
                                 (const float*)h->wrm.p, (float*)XW, N, P, 0, d->nnz_fea, M, 0);
-            if (h->dense_tc && fea_dense_tc_supported(N, M, P)) {
-                int rc = fea_dense_tc_launch((const float*)d->values_fea, (const float*)d->B, (float*)XW, N, M, P,
-                                             h->num_sms, h->stream);
-                if (rc == 0) { h->launches++; return 0; }
-                if (rc != -100) return fail(h, SGRACE_ECUDA, "tcgen05 dense FEA launch failed (%d)", rc);
-            }
-            dim3 grid((N + 63) / 64, (P + 63) / 64);
-            fea_dense_f32_kernel<<<grid, 256, 0, h->stream>>>((const float*)d->values_fea,
-                                                               (const float*)h->wrm.p, (float*)XW, N, M, P);
-            h->launches++;
-            CU(cudaGetLastError());
-            return 0;
+            return dense_f32(h, (const float*)d->values_fea, (const float*)d->B, (float*)XW, N, M, P, 0);
         }
         case SGRACE_MODE_F32_CSIM:
         case SGRACE_MODE_F16_CSIM:
@@ -597,6 +624,22 @@ int layer_run_impl(sgrace_handle* h, const sgrace_layer_desc* d, bool timed) {
     const int *rp_fea, *rp_adj;
     if (timed) CU(cudaEventRecord(h->ev[0], h->stream));
     if (int rc = resolve_rowptrs(h, d, &rp_fea, &rp_adj, true, true)) return rc;
+    // Opt-in aggregate-first order for a dense layer that widens (M_fea < P_w):  D = act((A.X).W).
+    // Equal to act(A.(X.W)) up to float rounding; gathers M_fea-wide rows instead of P_w-wide ones.
+    if (h->mode == SGRACE_MODE_F32_FAST && h->agg_first && d->gemm_mode == 1 && d->M_fea < d->P_w && d->M_fea % 4 == 0 &&
+        d->N_adj > 0 && d->P_w > 0) {
+        const int N = d->N_adj, M = d->M_fea, P = d->P_w;
+        if (!d->B || !d->values_fea || !d->D) return fail(h, SGRACE_EINVAL, "B / values_fea / D pointer not set");
+        if (int rc = ensure(h, h->ax, sizeof(float) * (size_t)N * M + 16)) return rc;
+        if (int rc = ensure(h, h->wrm, sizeof(float) * (size_t)M * P)) return rc;
+        if (int rc = transpose_b<float>(h, d->B, h->wrm.p, M, P)) return rc;
+        if (int rc = spmm_f32(h, rp_adj, d->columnIndex_adj, (const float*)d->values_adj, (const float*)d->values_fea,
+                              (float*)h->ax.p, N, M, 0, d->nnz_adj, 0, 0, N)) return rc;
+        if (timed) CU(cudaEventRecord(h->ev[1], h->stream));
+        if (int rc = dense_f32(h, (const float*)h->ax.p, (const float*)d->B, (float*)d->D, N, M, P, d->relu != 0)) return rc;
+        if (timed) CU(cudaEventRecord(h->ev[2], h->stream));
+        return 0;
+    }
     if (int rc = run_fea(h, d, rp_fea, XW)) return rc;
     if (timed) CU(cudaEventRecord(h->ev[1], h->stream));
     if (int rc = run_adj(h, d, rp_adj, XW, d->N_adj)) return rc;
@@ -752,7 +795,7 @@ int sgrace_destroy(sgrace_handle* h) {
         cudaFree(kv.second.dev);
         cudaFreeHost(kv.second.host);
     }
-    Scratch* all[] = {&h->wrm, &h->wdup, &h->xw, &h->wq, &h->s1, &h->s2, &h->rp_fea, &h->rp_adj, &h->lists, &h->counters};
+    Scratch* all[] = {&h->wrm, &h->wdup, &h->ax, &h->long_partial, &h->long_done, &h->xw, &h->wq, &h->s1, &h->s2, &h->rp_fea, &h->rp_adj, &h->lists, &h->counters};
     for (Scratch* s : all) if (s->p) cudaFree(s->p);
     if (h->max_fea_dev) cudaFree(h->max_fea_dev);
     for (int i = 0; i < 5; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -864,6 +907,7 @@ int sgrace_set_option(sgrace_handle* h, int key, int64_t v) {
         case SGRACE_OPT_VALIDATE: h->validate = v != 0; break;
         case SGRACE_OPT_DENSE_TC: h->dense_tc = v != 0; break;
         case SGRACE_OPT_STREAM_KERNEL: h->stream_kernel = v != 0; break;
+        case SGRACE_OPT_AGG_FIRST: h->agg_first = v != 0; break;
         default: return fail(h, SGRACE_EINVAL, "unknown option %d", key);
     }
     return SGRACE_OK;
@@ -887,6 +931,7 @@ int sgrace_get_option(sgrace_handle* h, int key, int64_t* v) {
         case SGRACE_OPT_VALIDATE: *v = h->validate; break;
         case SGRACE_OPT_DENSE_TC: *v = h->dense_tc; break;
         case SGRACE_OPT_STREAM_KERNEL: *v = h->stream_kernel; break;
+        case SGRACE_OPT_AGG_FIRST: *v = h->agg_first; break;
         default: return fail(h, SGRACE_EINVAL, "unknown option %d", key);
     }
     return SGRACE_OK;
@@ -933,6 +978,18 @@ int sgrace_adj_run(sgrace_handle* h, const sgrace_layer_desc* d, const void* XW_
     const int *rp_fea, *rp_adj;
     if (int rc = resolve_rowptrs(h, d, &rp_fea, &rp_adj, false, true)) return rc;
     return run_adj(h, d, rp_adj, XW_in, xw_rows);
+}
+
+int sgrace_dense_run(sgrace_handle* h, const void* X, const void* B, void* out, int32_t N, int32_t M, int32_t P, int32_t relu) {
+    if (!h) return SGRACE_EINVAL;
+    h->last_status = 0;
+    CU(cudaSetDevice(h->device));
+    if (h->mode != SGRACE_MODE_F32_FAST) return fail(h, SGRACE_EUNSUPPORTED, "sgrace_dense_run is a float32 fast-path entry");
+    if (!X || !B || !out || N < 0 || M <= 0 || P <= 0) return fail(h, SGRACE_EINVAL, "bad argument");
+    if (N == 0) return SGRACE_OK;
+    if (int rc = ensure(h, h->wrm, sizeof(float) * (size_t)M * P)) return rc;
+    if (int rc = transpose_b<float>(h, B, h->wrm.p, M, P)) return rc;
+    return dense_f32(h, (const float*)X, (const float*)B, (float*)out, N, M, P, relu != 0);
 }
 
 int sgrace_start(sgrace_handle* h) {

@@ -117,7 +117,8 @@ __device__ __forceinline__ void split4(float4 v, float4& hi, float4& lo) {
 template <int BK>
 __global__ void __launch_bounds__(THREADS, 1)
 fea_dense_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_b,
-                    const __grid_constant__ CUtensorMap map_o, int K, int P, int tiles, int ctas_per_slice, int kc, int ring) {
+                    const __grid_constant__ CUtensorMap map_o, int K, int P, int tiles, int ctas_per_slice, int kc, int ring,
+                    int relu) {
     constexpr int A_TILE = BM * BK * 4, B_TILE = BN * BK * 4;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -238,6 +239,10 @@ fea_dense_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             for (int blk = 0; blk < BN / 32; blk++) {
                 uint32_t r[32];
                 tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + ab * BN + blk * 32, r);
+                if (relu) {     // val = (acc > 0 || relu == 0) ? acc : 0  (kernelMatrixmult_all.cpp:2586-2590), aggregate-first order
+#pragma unroll
+                    for (int j = 0; j < 32; j++) r[j] = __uint_as_float(r[j]) > 0.f ? r[j] : 0u;
+                }
                 // the previous TMA store must have finished reading the staging tile
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 __syncwarp();
@@ -307,7 +312,7 @@ inline bool fea_dense_tc_supported(int N, int M, int P) {
 // returns 0 on success, -100 when the shape / pointers are not eligible (caller falls back), other
 // negatives on CUDA errors
 inline int fea_dense_tc_launch(const float* X, const float* B, float* out, int N, int M, int P, int num_sms, cudaStream_t stream,
-                               int force_bk = 0) {
+                               int force_bk = 0, int relu = 0) {
     if (!fea_dense_tc_supported(N, M, P)) return -100;
     if ((((uintptr_t)X) | ((uintptr_t)B) | ((uintptr_t)out)) & 15) return -100;
     int max_optin = 0, dev = 0;
@@ -337,10 +342,10 @@ inline int fea_dense_tc_launch(const float* X, const float* B, float* out, int N
     const size_t smem = tc::smem_bytes(bk, kc, ring);
     if (bk == 32) {
         if (cudaFuncSetAttribute(tc::fea_dense_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
-        tc::fea_dense_tc_kernel<32><<<per_slice * nslice, tc::THREADS, smem, stream>>>(mx, mb, mo, M, P, tiles, per_slice, kc, ring);
+        tc::fea_dense_tc_kernel<32><<<per_slice * nslice, tc::THREADS, smem, stream>>>(mx, mb, mo, M, P, tiles, per_slice, kc, ring, relu);
     } else {
         if (cudaFuncSetAttribute(tc::fea_dense_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
-        tc::fea_dense_tc_kernel<16><<<per_slice * nslice, tc::THREADS, smem, stream>>>(mx, mb, mo, M, P, tiles, per_slice, kc, ring);
+        tc::fea_dense_tc_kernel<16><<<per_slice * nslice, tc::THREADS, smem, stream>>>(mx, mb, mo, M, P, tiles, per_slice, kc, ring, relu);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }

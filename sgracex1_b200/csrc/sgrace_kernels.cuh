@@ -179,12 +179,11 @@ spmm_csr_f32_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
 // non-zeros; lanes own float4 column chunks (q = lane, lane+32, ...), warps' partials
 // are combined in warp order through shared memory -> deterministic.
 template <int NV>
-__global__ void __launch_bounds__(256)
-spmm_long_rows_f32_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
-                          const float* __restrict__ val, const float4* __restrict__ Bm,
-                          float4* __restrict__ out, int P4, int relu,
-                          const int* __restrict__ long_rows, const int* __restrict__ long_count) {
-    extern __shared__ float4 red[];               // [nwarp][P4]
+__device__ __forceinline__ void
+spmm_long_rows_per_row(const int* __restrict__ rowptr, const int* __restrict__ col,
+                       const float* __restrict__ val, const float4* __restrict__ Bm,
+                       float4* __restrict__ out, int P4, int relu,
+                       const int* __restrict__ long_rows, const int* __restrict__ long_count, float4* red) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int total = *long_count;
     for (int idx = blockIdx.x; idx < total; idx += gridDim.x) {
@@ -227,6 +226,141 @@ spmm_long_rows_f32_kernel(const int* __restrict__ rowptr, const int* __restrict_
                 r.z = r.z > 0.f ? r.z : 0.f; r.w = r.w > 0.f ? r.w : 0.f;
             }
             out[(size_t)row * P4 + q] = r;
+        }
+        __syncthreads();
+    }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256)
+spmm_long_rows_f32_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+                          const float* __restrict__ val, const float4* __restrict__ Bm,
+                          float4* __restrict__ out, int P4, int relu,
+                          const int* __restrict__ long_rows, const int* __restrict__ long_count) {
+    extern __shared__ float4 red[];               // [nwarp][P4]
+    spmm_long_rows_per_row<NV>(rowptr, col, val, Bm, out, P4, relu, long_rows, long_count, red);
+}
+
+// Long rows, segmented: the listed rows are cut into segments of SEG non-zeros; one CTA per segment
+// (grid-stride) writes the segment's partial row to `partial`, and the CTA that completes a row's
+// last segment adds the partials in segment order -- the result does not depend on which CTA that
+// is.  Balances power-law graphs (one 17 000-non-zero row no longer serialises a CTA) and keeps 4
+// gathers in flight per lane.  Every CTA rebuilds the (small) segment prefix of the list in shared
+// memory; lists longer than LONG_LIST_MAX take the row-per-CTA path above inside the same launch.
+constexpr int LONG_SEG = 256;
+constexpr int LONG_LIST_MAX = 8192;
+
+template <int NV>
+__global__ void __launch_bounds__(256)
+spmm_long_rows_seg_f32_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ val,
+                              const float4* __restrict__ Bm, float4* __restrict__ out, int P4, int relu,
+                              const int* __restrict__ long_rows, const int* __restrict__ long_count,
+                              float4* __restrict__ partial, int* __restrict__ row_done) {
+    extern __shared__ float4 red[];                               // [8 warps][P4]
+    __shared__ int pref[LONG_LIST_MAX + 1];
+    __shared__ int tsum[256];
+    __shared__ int is_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int count = *long_count;
+    if (count == 0) return;
+    if (count > LONG_LIST_MAX) {                                  // list too long for the shared prefix: row per CTA
+        spmm_long_rows_per_row<NV>(rowptr, col, val, Bm, out, P4, relu, long_rows, long_count, red);
+        return;
+    }
+    // ---- segment prefix over the list ----
+    const int per = (count + 255) / 256;
+    int local = 0;
+    for (int j = 0; j < per; j++) {
+        const int i = threadIdx.x * per + j;
+        if (i < count) { const int r = long_rows[i]; local += (rowptr[r + 1] - rowptr[r] + LONG_SEG - 1) / LONG_SEG; }
+    }
+    tsum[threadIdx.x] = local;
+    __syncthreads();
+    for (int off = 1; off < 256; off <<= 1) {
+        const int v = threadIdx.x >= off ? tsum[threadIdx.x - off] : 0;
+        __syncthreads();
+        tsum[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = tsum[threadIdx.x] - local;                          // exclusive prefix of this thread's entries
+    for (int j = 0; j < per; j++) {
+        const int i = threadIdx.x * per + j;
+        if (i < count) { pref[i] = run; const int r = long_rows[i]; run += (rowptr[r + 1] - rowptr[r] + LONG_SEG - 1) / LONG_SEG; }
+    }
+    if (threadIdx.x == 255) pref[count] = tsum[255];
+    __syncthreads();
+    const int total = pref[count];
+
+    for (int seg = blockIdx.x; seg < total; seg += gridDim.x) {
+        int lo = 0, hi = count;                                   // largest ri with pref[ri] <= seg
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pref[mid] <= seg) lo = mid; else hi = mid; }
+        const int ri = lo, row = long_rows[ri], s = seg - pref[ri], nseg = pref[ri + 1] - pref[ri];
+        const int kb = rowptr[row] + s * LONG_SEG, ke = min(rowptr[row + 1], kb + LONG_SEG);
+        // warp w takes non-zeros [kb + 32 w, kb + 32 w + 32)
+        float4 acc[NV];
+#pragma unroll
+        for (int v = 0; v < NV; v++) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int k0 = kb + wid * 32;
+        if (k0 < ke) {
+            int c = 0; float a = 0.f;
+            if (k0 + lane < ke) { c = __ldg(col + k0 + lane); a = __ldg(val + k0 + lane); }
+            const int cnt = min(32, ke - k0);
+            for (int i0 = 0; i0 < cnt; i0 += 4) {
+                float4 b[4][NV];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int ci = __shfl_sync(0xffffffffu, c, (i0 + i) & 31);
+                    const float4* brow = Bm + (size_t)ci * P4;
+#pragma unroll
+                    for (int v = 0; v < NV; v++) {
+                        const int q = v * 32 + lane;
+                        b[i][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (i0 + i < cnt && q < P4) b[i][v] = ldg4(brow + q);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float ai = __shfl_sync(0xffffffffu, a, (i0 + i) & 31);     // 0 past the segment end
+#pragma unroll
+                    for (int v = 0; v < NV; v++) fma4(acc[v], ai, b[i][v]);
+                }
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+            const int q = v * 32 + lane;
+            if (q < P4) red[wid * P4 + q] = acc[v];
+        }
+        __syncthreads();
+        for (int q = threadIdx.x; q < P4; q += blockDim.x) {
+            float4 r = red[q];
+            for (int w2 = 1; w2 < 8; w2++) {
+                const float4 t = red[w2 * P4 + q];
+                r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w;
+            }
+            partial[(size_t)seg * P4 + q] = r;
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            is_last = (atomicAdd(row_done + ri, 1) == nseg - 1);
+            if (is_last) row_done[ri] = 0;                        // counters are zero again when the launch ends
+        }
+        __syncthreads();
+        if (is_last) {
+            __threadfence();
+            for (int q = threadIdx.x; q < P4; q += blockDim.x) {
+                float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int s2 = 0; s2 < nseg; s2++) {
+                    const float4 t = __ldcg(partial + (size_t)(pref[ri] + s2) * P4 + q);
+                    r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w;
+                }
+                if (relu) {
+                    r.x = r.x > 0.f ? r.x : 0.f; r.y = r.y > 0.f ? r.y : 0.f;
+                    r.z = r.z > 0.f ? r.z : 0.f; r.w = r.w > 0.f ? r.w : 0.f;
+                }
+                out[(size_t)row * P4 + q] = r;
+            }
         }
         __syncthreads();
     }
@@ -278,7 +412,7 @@ spmm_csr_f32_scalar_kernel(const int* __restrict__ rowptr, const int* __restrict
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 fea_dense_f32_kernel(const float* __restrict__ X, const float* __restrict__ Wrm,
-                     float* __restrict__ out, int N, int M, int P) {
+                     float* __restrict__ out, int N, int M, int P, int relu) {
     __shared__ float xs[16][64 + 4];
     __shared__ float ws[16][64 + 4];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -321,7 +455,7 @@ fea_dense_f32_kernel(const float* __restrict__ X, const float* __restrict__ Wrm,
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             int c = c0 + tx * 4 + j;
-            if (c < P) out[(size_t)r * P + c] = acc[i][j];
+            if (c < P) out[(size_t)r * P + c] = (relu && !(acc[i][j] > 0.f)) ? 0.f : acc[i][j];
         }
     }
 }

@@ -53,6 +53,7 @@ struct StreamParams {
     int b_bytes;             // bytes of the Bm image staged in shared memory (SMEM*), multiple of 16
     int streaming_store;     // 1: out is not re-read soon (D) -> st.global.cs
     int static_tiles;        // tiles each CTA owns as one contiguous run before it claims dynamically
+    int l1_prefetch;         // GLOBAL gathers: passes of next-row Bm prefetch per group (0 = off)
     int dry_run;             // debug: stream the stages but skip the arithmetic (feed-rate measurement)
     int prefetch_rows;       // > 0 (GLOBAL): rows of Bm; the producer L2-prefetches Bm rows [rb, re) of a sub-tile
     int* long_rows;
@@ -369,6 +370,22 @@ spmm_stream_f32_kernel(const StreamParams p) {
 
         for (int i = cw * RPW + g; i < h.nrows && !p.dry_run; i += ncw * RPW) {
             const int beg = rp_s[i], end = rp_s[i + 1];
+            if (BSRC == BSRC_GLOBAL && p.l1_prefetch) {
+                // Software pipelining without registers: pull the Bm rows of the group's NEXT row towards
+                // this SM while the current row is processed (a group of LPR lanes covers LPR non-zeros
+                // per pass, `l1_prefetch` passes; each lane touches its own 16-byte chunk of the row).
+                const int inext = i + ncw * RPW;
+                if (inext < h.nrows) {
+                    const int nb = rp_s[inext], ne = rp_s[inext + 1];
+                    for (int pass = 0, k = nb + l; pass < p.l1_prefetch && k < ne; pass++, k += LPR) {
+                        const int c = col_k[k];
+#pragma unroll
+                        for (int v = 0; v < NV; v++)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(bg_lane - (size_t)l * 16 + (size_t)(unsigned)c * rowbytes +
+                                                                             (size_t)((v * LPR + (l & (LPR - 1))) * 16)));
+                    }
+                }
+            }
             float4 acc[NV];
 #pragma unroll
             for (int v = 0; v < NV; v++) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -346,6 +346,12 @@ def test_dense_fea_tensor_core_path(ip, shape):
         got[tcore] = (dl.result("XW").copy(), dl.result("D").copy())
         U.assert_close_f32(got[tcore][0], ref_xw, what=f"dense FEA XW tensor_core={tcore} {shape}")
         U.assert_close_f32(got[tcore][1], ref_d, what=f"dense layer D tensor_core={tcore} {shape}")
-    ip.configure(dense_tc=1, staging=1)
+    # opt-in aggregate-first order act((A.X).W): same result to float tolerance
+    ip.configure(dense_tc=1, agg_first=1)
+    dl = DeviceLayer(ip.handle, _lib.MODE_F32_FAST)
+    dl.load(N=n, M=m, P=p, adj=adj, x_dense=x, B=O.weights_to_B(w), relu=1)
+    dl.run()
+    U.assert_close_f32(dl.result("D"), ref_d, what=f"aggregate-first dense layer {shape}")
+    ip.configure(dense_tc=1, staging=1, agg_first=0)
     # the two paths are different arithmetic (3xTF32 vs FMA) and must agree to float tolerance
     U.assert_close_f32(got[1][0], got[0][0], rtol=1e-5, what="tensor-core vs CUDA-core XW")

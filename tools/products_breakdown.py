@@ -41,3 +41,19 @@ print(f"ADJ       {ta:.3f} ms  {ab / ta / 1e6:.0f} GB/s algorithmic, gather {len
 ref = torch.relu(torch.sparse_csr_tensor(adj[0].long(), adj[1].long(), adj[2], size=(N, N)) @ (x @ W))
 err = (D - ref).abs().max().item() / ref.abs().max().item()
 print("max rel err vs torch", err)
+
+# aggregate-first order through the layer entry point
+from sgracex1_b200.driver import DeviceLayer  # noqa: E402
+h.set_option(_lib.OPT_AGG_FIRST, 1)
+d = _lib.LayerDesc()
+d.gemm_mode, d.relu, d.N_adj, d.M_adj, d.M_fea, d.P_w = 1, 1, N, N, M, P
+Bt = W.t().contiguous()
+D2 = torch.empty(N, P, device=dev)
+d.values_fea, d.B, d.D = x.data_ptr(), Bt.data_ptr(), D2.data_ptr()
+d.rowPtr_adj, d.columnIndex_adj, d.values_adj, d.nnz_adj = adj[0].data_ptr(), adj[1].data_ptr(), adj[2].data_ptr(), len(ci)
+for it in range(4):
+    ev[0].record()
+    h.layer_run(d)
+    ev[1].record()
+    torch.cuda.synchronize()
+print(f"aggregate-first layer {ev[0].elapsed_time(ev[1]):.3f} ms; max rel err vs torch {(D2 - ref).abs().max().item() / ref.abs().max().item():.2e}")

@@ -1,3 +1,4 @@
 exec > gpurun_out/run3.log 2>&1
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --workload products --steps 3 --warmup 3 2>&1 | grep '^{' | cut -c1-200
+python tools/products_breakdown.py 1.0 2>&1 | grep -v Warn | grep -v "ref = "
+python bench.py --steps 20 --warmup 3 --no-cpu 2>&1 | python tools/brief.py
