@@ -346,6 +346,8 @@ def main():
     ap.add_argument("--graphs", type=int, default=0, help="molecule workload: graphs per step per GPU (default 188*64)")
     ap.add_argument("--hidden", type=int, default=0, help="molecule workload: hidden width (default 64)")
     ap.add_argument("--scale", type=float, default=1.0, help="products workload: fraction of the 2.45M-node shape")
+    ap.add_argument("--order", default="agg_first", choices=["agg_first", "reference"],
+                    help="products workload: act((A.X).W) (opt-in order, peer gathers over NVLink) or act(A.(X.W)) (all-gather)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -82,6 +82,8 @@ enum {
     SGRACE_OPT_DENSE_TC = 14,       /* 1: allow the tcgen05 path for wide dense FEA (FAST)  */
     SGRACE_OPT_STREAM_KERNEL = 15,  /* 1 (default): TMA-staged persistent SpMM kernel (FAST);
                                        0: the row-strided kernel (any pointer alignment)    */
+    SGRACE_OPT_ACCUMULATE = 17,     /* 1: the ADJ stage computes D = act(D + A.XW): the second pass over an
+                                       adjacency split by column ownership (multi-GPU halo)  */
     SGRACE_OPT_AGG_FIRST = 16       /* 1: dense layers with M_fea < P_w run as act((A.X).W) --
                                        equal up to float rounding, gathers narrower rows;
                                        0 (default): the reference's order act(A.(X.W))      */
@@ -190,6 +192,21 @@ int sgrace_adj_run(sgrace_handle* h, const sgrace_layer_desc* d, const void* XW_
  * multi-GPU callers of the aggregate-first order, where the activation follows the dense stage */
 int sgrace_dense_run(sgrace_handle* h, const void* X, const void* B, void* out, int32_t N, int32_t M, int32_t P,
                      int32_t relu);
+
+/* ---- multi-GPU: the ADJ stage gathering a ROW-PARTITIONED XW (or X) straight over NVLink ----
+ * rank r of n_peers holds rows [r*block_rows, (r+1)*block_rows) of the gathered matrix in a buffer
+ * from sgrace_peer_alloc; every rank opens the others' buffers with the 64-byte handles (exchanged
+ * by the caller, e.g. torch.distributed.all_gather_object) and passes the table of n_peers device
+ * addresses, its own included.  No all-gather: only the rows an adjacency row references move. */
+int sgrace_peer_alloc(sgrace_handle* h, size_t bytes, uint64_t* device_addr, unsigned char handle_out[64]);
+int sgrace_peer_open(sgrace_handle* h, const unsigned char handle_in[64], uint64_t* device_addr);
+int sgrace_peer_release(sgrace_handle* h);     /* closes every mapping and frees every peer buffer of h */
+int sgrace_adj_run_peer(sgrace_handle* h, const sgrace_layer_desc* d, const uint64_t* bases, int32_t n_peers,
+                        int32_t block_rows);
+/* halo exchange: copy `n_rows` listed rows (global row ids, int32, device memory) of the partitioned
+ * float32 matrix (`width` floats per row, multiple of 4) from their owners into `dst` (device) */
+int sgrace_halo_gather(sgrace_handle* h, const uint64_t* bases, int32_t n_peers, int32_t block_rows, const int32_t* rows,
+                       int64_t n_rows, int32_t width, void* dst);
 
 /* number of this library's kernels launched on the handle since creation (bench evidence) */
 int sgrace_launch_count(sgrace_handle* h, uint64_t* count);

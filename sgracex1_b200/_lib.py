@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libsgrace_b200.so")
 MODE_F32_FAST, MODE_F32_CSIM, MODE_F16_CSIM, MODE_FIX16_CSIM, MODE_FULL = 0, 1, 2, 3, 4
 (OPT_MODE, OPT_SPMM_BLOCK, OPT_LAT_FEA, OPT_LAT_ADJ, OPT_FEA_THREADS, OPT_ADJ_THREADS,
  OPT_USE_SBLOCKS, OPT_INDEX_FORMAT, OPT_QBITS, OPT_STAGING, OPT_LONG_ROW, OPT_LEAKY_ALPHA_BITS,
- OPT_VALIDATE, OPT_DENSE_TC, OPT_STREAM_KERNEL, OPT_AGG_FIRST) = range(1, 17)
+ OPT_VALIDATE, OPT_DENSE_TC, OPT_STREAM_KERNEL, OPT_AGG_FIRST, OPT_ACCUMULATE) = range(1, 18)
 REG_CTRL, REG_MAX_FEA = 0x00, 0x70
 
 EXPORTS = (
@@ -23,7 +23,8 @@ EXPORTS = (
     "sgrace_read_reg", "sgrace_write_reg64", "sgrace_reg_offset", "sgrace_set_option",
     "sgrace_get_option", "sgrace_set_stream", "sgrace_start", "sgrace_done", "sgrace_wait",
     "sgrace_stage_times", "sgrace_layer_run", "sgrace_fea_run", "sgrace_adj_run",
-    "sgrace_launch_count", "sgrace_dense_run",
+    "sgrace_launch_count", "sgrace_dense_run", "sgrace_peer_alloc", "sgrace_peer_open", "sgrace_peer_release",
+    "sgrace_adj_run_peer", "sgrace_halo_gather",
 )
 
 
@@ -88,6 +89,11 @@ def load():
     lib.sgrace_fea_run.argtypes = [H, C.POINTER(LayerDesc), C.c_void_p]
     lib.sgrace_adj_run.argtypes = [H, C.POINTER(LayerDesc), C.c_void_p, C.c_int32]
     lib.sgrace_launch_count.argtypes = [H, C.POINTER(C.c_uint64)]
+    lib.sgrace_peer_alloc.argtypes = [H, C.c_size_t, C.POINTER(C.c_uint64), C.c_char_p]
+    lib.sgrace_peer_open.argtypes = [H, C.c_char_p, C.POINTER(C.c_uint64)]
+    lib.sgrace_peer_release.argtypes = [H]
+    lib.sgrace_adj_run_peer.argtypes = [H, C.POINTER(LayerDesc), C.POINTER(C.c_uint64), C.c_int32, C.c_int32]
+    lib.sgrace_halo_gather.argtypes = [H, C.POINTER(C.c_uint64), C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     lib.sgrace_dense_run.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     for name in EXPORTS:
         if name not in ("sgrace_last_error", "sgrace_version"):
@@ -202,6 +208,31 @@ class Handle:
     def dense_run(self, x_ptr, b_ptr, out_ptr, N, M, P, relu=0):
         self._ck(self.lib.sgrace_dense_run(self.h, C.c_void_p(x_ptr), C.c_void_p(b_ptr), C.c_void_p(out_ptr), int(N), int(M),
                                            int(P), int(relu)))
+
+    # peer memory (multi-GPU gathers over NVLink) --------------------------------
+    def peer_alloc(self, nbytes):
+        """Device buffer other ranks can map: returns (device address, 64-byte IPC handle)."""
+        addr = C.c_uint64()
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.sgrace_peer_alloc(self.h, int(nbytes), C.byref(addr), buf))
+        return int(addr.value), buf.raw
+
+    def peer_open(self, handle_bytes):
+        addr = C.c_uint64()
+        self._ck(self.lib.sgrace_peer_open(self.h, C.create_string_buffer(bytes(handle_bytes), 64), C.byref(addr)))
+        return int(addr.value)
+
+    def peer_release(self):
+        self._ck(self.lib.sgrace_peer_release(self.h))
+
+    def adj_run_peer(self, desc: LayerDesc, bases, block_rows):
+        arr = (C.c_uint64 * len(bases))(*[int(b) for b in bases])
+        self._ck(self.lib.sgrace_adj_run_peer(self.h, C.byref(desc), arr, len(bases), int(block_rows)))
+
+    def halo_gather(self, bases, block_rows, rows_ptr, n_rows, width, dst_ptr):
+        arr = (C.c_uint64 * len(bases))(*[int(b) for b in bases])
+        self._ck(self.lib.sgrace_halo_gather(self.h, arr, len(bases), int(block_rows), C.c_void_p(rows_ptr), int(n_rows),
+                                             int(width), C.c_void_p(dst_ptr)))
 
     def launch_count(self):
         v = C.c_uint64()

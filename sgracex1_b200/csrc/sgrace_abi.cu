@@ -48,7 +48,12 @@ struct sgrace_handle {
     // options
     int mode = SGRACE_MODE_F32_FAST;
     int spmm_block = 1, lat_fea = 0, lat_adj = 0, fea_threads = 1, adj_threads = 1, use_sblocks = 0;
-    int index_format = 0, qbits = 8, staging = 1, long_row = 512, validate = 0, dense_tc = 1, stream_kernel = 1, agg_first = 0;
+    int index_format = 0, qbits = 8, staging = 1, long_row = 512, validate = 0, dense_tc = 1, stream_kernel = 1, agg_first = 0, accumulate = 0;
+    // set for the duration of sgrace_adj_run_peer
+    const char* peer_base[MAX_PEERS] = {nullptr};
+    int peer_block = 0, peer_count = 0;
+    std::map<uint64_t, size_t> peer_allocs;     // device buffers from sgrace_peer_alloc
+    std::vector<uint64_t> peer_opened;          // mappings from sgrace_peer_open
     float leaky_alpha = 0.2f;
     // scratch (grow-only)
     Scratch wrm, wdup, ax, long_partial, long_done, xw, wq, s1, s2, rp_fea, rp_adj, lists, counters;
@@ -130,6 +135,10 @@ int launch_long_rows(sgrace_handle* h, const int* rp, const int* ci, const float
     const long long max_segs = nnz_hint > 0 ? nnz_hint / LONG_SEG + max_rows + 1 : 0;
     const size_t part_bytes = (size_t)max_segs * P4 * sizeof(float4);
     const bool seg = nnz_hint > 0 && part_bytes <= ((size_t)1 << 30) && !env_int("SGRACE_LONG_NOSEG", 0);
+    PeerTable pt;
+    memset(&pt, 0, sizeof(pt));
+    pt.count = h->peer_count; pt.block = h->peer_block; pt.accumulate = h->accumulate;
+    for (int r = 0; r < 8; r++) pt.base[r] = h->peer_base[r];
     if (seg) {
         if (int rc = ensure(h, h->long_partial, part_bytes + 16)) return rc;
         // per-row completion counters: zeroed once when (re)allocated, reset by the kernel after use
@@ -142,12 +151,12 @@ int launch_long_rows(sgrace_handle* h, const int* rp, const int* ci, const float
             CU(cudaFuncSetAttribute(spmm_long_rows_seg_f32_kernel<NVL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
         spmm_long_rows_seg_f32_kernel<NVL><<<h->num_sms * 4, 256, lsmem, h->stream>>>(
             rp, ci, va, (const float4*)Bm, (float4*)out, P4, relu, long_rows, long_count, (float4*)h->long_partial.p,
-            (int*)h->long_done.p);
+            (int*)h->long_done.p, pt);
     } else {
         if (lsmem > 48 * 1024)
             CU(cudaFuncSetAttribute(spmm_long_rows_f32_kernel<NVL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
         spmm_long_rows_f32_kernel<NVL><<<h->num_sms * 2, 256, lsmem, h->stream>>>(
-            rp, ci, va, (const float4*)Bm, (float4*)out, P4, relu, long_rows, long_count);
+            rp, ci, va, (const float4*)Bm, (float4*)out, P4, relu, long_rows, long_count, pt);
     }
     h->launches++;
     CU(cudaGetLastError());
@@ -210,6 +219,7 @@ int launch_spmm_stream(sgrace_handle* h, const int* rp, const int* ci, const flo
     sp.rowptr = rp; sp.col = ci; sp.val = va; sp.out = (float4*)out;
     sp.nrows = nrows; sp.P4 = P4; sp.relu = relu;
     sp.streaming_store = final_out;
+    sp.accumulate = h->accumulate;
     sp.long_rows = long_rows; sp.long_count = long_count; sp.tile_counter = tile_counter;
     sp.long_thresh = h->long_row;
     const bool exact = (P4 == LPR * NV);
@@ -295,6 +305,27 @@ int launch_spmm_stream(sgrace_handle* h, const int* rp, const int* ci, const flo
         if (LPR == 4 && NV == 1) STREAM_LAUNCH(BSRC_SMEM_DUP, 1024, 1, true);
     } else if (bsrc == BSRC_SMEM) {
         if (exact) STREAM_LAUNCH(BSRC_SMEM, MT_SMEM, 1, true); else STREAM_LAUNCH(BSRC_SMEM, 512, 1, false);
+    } else if (h->peer_count > 0) {
+        // row-partitioned Bm gathered over NVLink; only wide rows (a full warp per row) are instantiated
+        sp.peer_count = h->peer_count; sp.peer_block = h->peer_block;
+        for (int r = 0; r < MAX_PEERS; r++) sp.peer_base[r] = h->peer_base[r];
+        if (LPR != 32) return fail(h, SGRACE_EUNSUPPORTED, "peer gathers need P_w >= 68 (one warp per row)");
+#define STREAM_LAUNCH_PEER(MT, MB, EX)                                                                         \
+        do {                                                                                                   \
+            auto kern = spmm_stream_f32_kernel<LPR, NV, BSRC_GLOBAL, MT, MB, EX, true>;                        \
+            int threads = MT > 384 ? 384 : MT;                                                                 \
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+            int per_sm = 1;                                                                                    \
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));                   \
+            if (per_sm < 1) return fail(h, SGRACE_ECUDA, "streaming SpMM does not fit an SM");                 \
+            const long long tiles = ((long long)nrows + TR - 1) / TR;                                          \
+            long long grid = (long long)h->num_sms * per_sm;                                                   \
+            if (grid > tiles) grid = tiles;                                                                    \
+            sp.static_tiles = 0;                                                                               \
+            kern<<<(int)grid, threads, smem, h->stream>>>(sp);                                                 \
+        } while (0)
+        if (LPR == 32) { if (exact) STREAM_LAUNCH_PEER(512, MB_GLOB, true); else STREAM_LAUNCH_PEER(512, 1, false); }
+#undef STREAM_LAUNCH_PEER
     } else {
         if (exact) STREAM_LAUNCH(BSRC_GLOBAL, 512, MB_GLOB, true); else STREAM_LAUNCH(BSRC_GLOBAL, 512, 1, false);
     }
@@ -339,6 +370,8 @@ int spmm_f32(sgrace_handle* h, const int* rp, const int* ci, const float* va, co
 #undef SGRACE_STREAM
         return fail(h, SGRACE_EUNSUPPORTED, "P_w=%d > 1024 not supported", P);
     }
+    if (h->peer_count > 0 || h->accumulate)
+        return fail(h, SGRACE_EUNSUPPORTED, "peer gathers / accumulate need 16-byte aligned CSR arrays and P_w a multiple of 4");
     if (aligned) {
         const int P4 = P / 4;
         if (P4 == 1) return launch_spmm_vec<1, 1>(h, rp, ci, va, Bm, out, nrows, P, relu);
@@ -908,6 +941,7 @@ int sgrace_set_option(sgrace_handle* h, int key, int64_t v) {
         case SGRACE_OPT_DENSE_TC: h->dense_tc = v != 0; break;
         case SGRACE_OPT_STREAM_KERNEL: h->stream_kernel = v != 0; break;
         case SGRACE_OPT_AGG_FIRST: h->agg_first = v != 0; break;
+        case SGRACE_OPT_ACCUMULATE: h->accumulate = v != 0; break;
         default: return fail(h, SGRACE_EINVAL, "unknown option %d", key);
     }
     return SGRACE_OK;
@@ -932,6 +966,7 @@ int sgrace_get_option(sgrace_handle* h, int key, int64_t* v) {
         case SGRACE_OPT_DENSE_TC: *v = h->dense_tc; break;
         case SGRACE_OPT_STREAM_KERNEL: *v = h->stream_kernel; break;
         case SGRACE_OPT_AGG_FIRST: *v = h->agg_first; break;
+        case SGRACE_OPT_ACCUMULATE: *v = h->accumulate; break;
         default: return fail(h, SGRACE_EINVAL, "unknown option %d", key);
     }
     return SGRACE_OK;
@@ -990,6 +1025,82 @@ int sgrace_dense_run(sgrace_handle* h, const void* X, const void* B, void* out, 
     if (int rc = ensure(h, h->wrm, sizeof(float) * (size_t)M * P)) return rc;
     if (int rc = transpose_b<float>(h, B, h->wrm.p, M, P)) return rc;
     return dense_f32(h, (const float*)X, (const float*)B, (float*)out, N, M, P, relu != 0);
+}
+
+int sgrace_peer_alloc(sgrace_handle* h, size_t bytes, uint64_t* device_addr, unsigned char handle_out[64]) {
+    if (!h || !device_addr || !handle_out) return SGRACE_EINVAL;
+    CU(cudaSetDevice(h->device));
+    void* p = nullptr;
+    CU(cudaMalloc(&p, bytes ? bytes : 1));
+    cudaIpcMemHandle_t ipc;
+    cudaError_t e = cudaIpcGetMemHandle(&ipc, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(h, SGRACE_ECUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e)); }
+    static_assert(sizeof(ipc) == 64, "IPC handle size");
+    memcpy(handle_out, &ipc, 64);
+    h->peer_allocs[(uint64_t)(uintptr_t)p] = bytes;
+    *device_addr = (uint64_t)(uintptr_t)p;
+    return SGRACE_OK;
+}
+
+int sgrace_peer_open(sgrace_handle* h, const unsigned char handle_in[64], uint64_t* device_addr) {
+    if (!h || !handle_in || !device_addr) return SGRACE_EINVAL;
+    CU(cudaSetDevice(h->device));
+    cudaIpcMemHandle_t ipc;
+    memcpy(&ipc, handle_in, 64);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_opened.push_back((uint64_t)(uintptr_t)p);
+    *device_addr = (uint64_t)(uintptr_t)p;
+    return SGRACE_OK;
+}
+
+int sgrace_peer_release(sgrace_handle* h) {
+    if (!h) return SGRACE_EINVAL;
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    for (uint64_t a : h->peer_opened) cudaIpcCloseMemHandle((void*)(uintptr_t)a);
+    h->peer_opened.clear();
+    for (auto& kv : h->peer_allocs) cudaFree((void*)(uintptr_t)kv.first);
+    h->peer_allocs.clear();
+    return SGRACE_OK;
+}
+
+int sgrace_halo_gather(sgrace_handle* h, const uint64_t* bases, int32_t n_peers, int32_t block_rows, const int32_t* rows,
+                       int64_t n_rows, int32_t width, void* dst) {
+    if (!h) return SGRACE_EINVAL;
+    h->last_status = 0;
+    CU(cudaSetDevice(h->device));
+    if (!bases || n_peers < 1 || n_peers > MAX_PEERS || block_rows < 1 || width < 4 || width % 4 || n_rows < 0 || (n_rows && (!rows || !dst)))
+        return fail(h, SGRACE_EINVAL, "bad halo-gather argument");
+    if (n_rows == 0) return SGRACE_OK;
+    PeerTable pt;
+    memset(&pt, 0, sizeof(pt));
+    pt.count = n_peers; pt.block = block_rows;
+    for (int r = 0; r < n_peers; r++) pt.base[r] = (const char*)(uintptr_t)bases[r];
+    const long long total = (long long)n_rows * (width / 4);
+    long long grid = (total + 255) / 256;
+    if (grid > (long long)h->num_sms * 8) grid = (long long)h->num_sms * 8;
+    halo_gather_kernel<<<(int)grid, 256, 0, h->stream>>>(pt, rows, n_rows, width / 4, (float4*)dst);
+    h->launches++;
+    CU(cudaGetLastError());
+    return SGRACE_OK;
+}
+
+int sgrace_adj_run_peer(sgrace_handle* h, const sgrace_layer_desc* d, const uint64_t* bases, int32_t n_peers,
+                        int32_t block_rows) {
+    if (!h) return SGRACE_EINVAL;
+    h->last_status = 0;
+    CU(cudaSetDevice(h->device));
+    if (int rc = check_desc(h, d)) return rc;
+    if (!bases || n_peers < 1 || n_peers > MAX_PEERS || block_rows < 1) return fail(h, SGRACE_EINVAL, "bad peer table");
+    if (h->mode != SGRACE_MODE_F32_FAST) return fail(h, SGRACE_EUNSUPPORTED, "peer gathers are a float32 fast-path feature");
+    const int *rp_fea, *rp_adj;
+    if (int rc = resolve_rowptrs(h, d, &rp_fea, &rp_adj, false, true)) return rc;
+    for (int r = 0; r < MAX_PEERS; r++) h->peer_base[r] = r < n_peers ? (const char*)(uintptr_t)bases[r] : nullptr;
+    h->peer_block = block_rows; h->peer_count = n_peers;
+    const int rc = run_adj(h, d, rp_adj, (const void*)(uintptr_t)bases[0], n_peers * block_rows);
+    h->peer_count = 0;
+    return rc;
 }
 
 int sgrace_start(sgrace_handle* h) {

@@ -27,6 +27,19 @@ __device__ __forceinline__ void fma4(float4& a, float s, const float4& b) {
     a.z = fmaf(s, b.z, a.z); a.w = fmaf(s, b.w, a.w);
 }
 
+// Row-partitioned Bm for multi-GPU gathers: rank r holds rows [r*block, (r+1)*block) at base[r]
+struct PeerTable {
+    const char* base[8];
+    int block;
+    int count;      // 0: Bm is one local matrix
+    int accumulate; // 1: the kernels add to `out` instead of overwriting it (second pass of a split adjacency)
+};
+__device__ __forceinline__ const float4* bm_row(const float4* Bm, const PeerTable& pt, int c, int P4) {
+    if (pt.count == 0) return Bm + (size_t)c * P4;
+    const int r = c / pt.block;
+    return reinterpret_cast<const float4*>(pt.base[r]) + (size_t)(c - r * pt.block) * P4;
+}
+
 // streaming store: D / XW rows are written once and not re-read by this kernel
 __device__ __forceinline__ void st_cs4(float4* p, const float4& v) { __stcs(p, v); }
 
@@ -183,7 +196,8 @@ __device__ __forceinline__ void
 spmm_long_rows_per_row(const int* __restrict__ rowptr, const int* __restrict__ col,
                        const float* __restrict__ val, const float4* __restrict__ Bm,
                        float4* __restrict__ out, int P4, int relu,
-                       const int* __restrict__ long_rows, const int* __restrict__ long_count, float4* red) {
+                       const int* __restrict__ long_rows, const int* __restrict__ long_count, float4* red,
+                       const PeerTable& pt) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int total = *long_count;
     for (int idx = blockIdx.x; idx < total; idx += gridDim.x) {
@@ -201,11 +215,11 @@ spmm_long_rows_per_row(const int* __restrict__ rowptr, const int* __restrict__ c
             for (int i = 0; i < cnt; i++) {
                 const int ci = __shfl_sync(0xffffffffu, c, i);
                 const float ai = __shfl_sync(0xffffffffu, a, i);
-                const float4* brow = Bm + (size_t)ci * P4;
+                const float4* brow = bm_row(Bm, pt, ci, P4);
 #pragma unroll
                 for (int v = 0; v < NV; v++) {
                     const int q = v * 32 + lane;
-                    if (q < P4) fma4(acc[v], ai, ldg4(brow + q));
+                    if (q < P4) fma4(acc[v], ai, pt.count ? __ldcg(brow + q) : ldg4(brow + q));
                 }
             }
         }
@@ -221,6 +235,7 @@ spmm_long_rows_per_row(const int* __restrict__ rowptr, const int* __restrict__ c
                 const float4 t = red[w2 * P4 + q];
                 r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w;
             }
+            if (pt.accumulate) { const float4 o = out[(size_t)row * P4 + q]; r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
             if (relu) {
                 r.x = r.x > 0.f ? r.x : 0.f; r.y = r.y > 0.f ? r.y : 0.f;
                 r.z = r.z > 0.f ? r.z : 0.f; r.w = r.w > 0.f ? r.w : 0.f;
@@ -236,9 +251,9 @@ __global__ void __launch_bounds__(256)
 spmm_long_rows_f32_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
                           const float* __restrict__ val, const float4* __restrict__ Bm,
                           float4* __restrict__ out, int P4, int relu,
-                          const int* __restrict__ long_rows, const int* __restrict__ long_count) {
+                          const int* __restrict__ long_rows, const int* __restrict__ long_count, const PeerTable pt) {
     extern __shared__ float4 red[];               // [nwarp][P4]
-    spmm_long_rows_per_row<NV>(rowptr, col, val, Bm, out, P4, relu, long_rows, long_count, red);
+    spmm_long_rows_per_row<NV>(rowptr, col, val, Bm, out, P4, relu, long_rows, long_count, red, pt);
 }
 
 // Long rows, segmented: the listed rows are cut into segments of SEG non-zeros; one CTA per segment
@@ -255,7 +270,7 @@ __global__ void __launch_bounds__(256)
 spmm_long_rows_seg_f32_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ val,
                               const float4* __restrict__ Bm, float4* __restrict__ out, int P4, int relu,
                               const int* __restrict__ long_rows, const int* __restrict__ long_count,
-                              float4* __restrict__ partial, int* __restrict__ row_done) {
+                              float4* __restrict__ partial, int* __restrict__ row_done, const PeerTable pt) {
     extern __shared__ float4 red[];                               // [8 warps][P4]
     __shared__ int pref[LONG_LIST_MAX + 1];
     __shared__ int tsum[256];
@@ -264,7 +279,7 @@ spmm_long_rows_seg_f32_kernel(const int* __restrict__ rowptr, const int* __restr
     const int count = *long_count;
     if (count == 0) return;
     if (count > LONG_LIST_MAX) {                                  // list too long for the shared prefix: row per CTA
-        spmm_long_rows_per_row<NV>(rowptr, col, val, Bm, out, P4, relu, long_rows, long_count, red);
+        spmm_long_rows_per_row<NV>(rowptr, col, val, Bm, out, P4, relu, long_rows, long_count, red, pt);
         return;
     }
     // ---- segment prefix over the list ----
@@ -310,12 +325,12 @@ spmm_long_rows_seg_f32_kernel(const int* __restrict__ rowptr, const int* __restr
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     const int ci = __shfl_sync(0xffffffffu, c, (i0 + i) & 31);
-                    const float4* brow = Bm + (size_t)ci * P4;
+                    const float4* brow = bm_row(Bm, pt, ci, P4);
 #pragma unroll
                     for (int v = 0; v < NV; v++) {
                         const int q = v * 32 + lane;
                         b[i][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (i0 + i < cnt && q < P4) b[i][v] = ldg4(brow + q);
+                        if (i0 + i < cnt && q < P4) b[i][v] = pt.count ? __ldcg(brow + q) : ldg4(brow + q);
                     }
                 }
 #pragma unroll
@@ -350,7 +365,7 @@ spmm_long_rows_seg_f32_kernel(const int* __restrict__ rowptr, const int* __restr
         if (is_last) {
             __threadfence();
             for (int q = threadIdx.x; q < P4; q += blockDim.x) {
-                float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 r = pt.accumulate ? out[(size_t)row * P4 + q] : make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int s2 = 0; s2 < nseg; s2++) {
                     const float4 t = __ldcg(partial + (size_t)(pref[ri] + s2) * P4 + q);
                     r.x += t.x; r.y += t.y; r.z += t.z; r.w += t.w;
@@ -363,6 +378,22 @@ spmm_long_rows_seg_f32_kernel(const int* __restrict__ rowptr, const int* __restr
             }
         }
         __syncthreads();
+    }
+}
+
+// Halo gather for a row-partitioned matrix: copy the listed rows (global row ids, owner = id / block)
+// from the owners' peer-mapped buffers into a local contiguous buffer.  One thread per 16 bytes, so
+// hundreds of thousands of independent loads are in flight -- what NVLink latency (~2-3 us) needs.
+__global__ void __launch_bounds__(256)
+halo_gather_kernel(const PeerTable pt, const int* __restrict__ rows, long long n_rows, int W4, float4* __restrict__ dst) {
+    const long long total = n_rows * W4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long j = i / W4;
+        const int q = (int)(i - j * W4);
+        const int c = __ldg(rows + j);
+        const int r = c / pt.block;
+        const float4* src = reinterpret_cast<const float4*>(pt.base[r]) + (size_t)(c - r * pt.block) * W4 + q;
+        dst[i] = __ldcg(src);
     }
 }
 

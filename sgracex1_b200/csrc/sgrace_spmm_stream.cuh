@@ -37,6 +37,7 @@
 namespace sgrace {
 
 enum { BSRC_GLOBAL = 0, BSRC_SMEM = 1, BSRC_SMEM_DUP = 2 };
+constexpr int MAX_PEERS = 8;
 
 struct StreamParams {
     const int* rowptr;
@@ -52,6 +53,7 @@ struct StreamParams {
     int groups;              // G: independent producer/consumer pipelines per CTA
     int b_bytes;             // bytes of the Bm image staged in shared memory (SMEM*), multiple of 16
     int streaming_store;     // 1: out is not re-read soon (D) -> st.global.cs
+    int accumulate;          // 1: out = act(out + A.Bm)  (second pass over a split adjacency)
     int static_tiles;        // tiles each CTA owns as one contiguous run before it claims dynamically
     int l1_prefetch;         // GLOBAL gathers: passes of next-row Bm prefetch per group (0 = off)
     int dry_run;             // debug: stream the stages but skip the arithmetic (feed-rate measurement)
@@ -59,6 +61,11 @@ struct StreamParams {
     int* long_rows;
     int* long_count;
     int* tile_counter;
+    // PEER gathers: Bm is row-partitioned over `peer_count` GPUs, rank r holds rows [r*peer_block, (r+1)*peer_block)
+    // at peer_base[r] (its own buffer or a peer-mapped one): the gather goes straight over NVLink
+    const char* peer_base[MAX_PEERS];
+    int peer_block;
+    int peer_count;
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -136,7 +143,7 @@ inline size_t stream_smem_bytes(int groups, int stages, int tile_rows, int stage
 }
 
 // EXACT: P4 == LPR*NV, so every lane owns live columns and the row stride of Bm is a constant.
-template <int LPR, int NV, int BSRC, int MAXT, int MINB, bool EXACT>
+template <int LPR, int NV, int BSRC, int MAXT, int MINB, bool EXACT, bool PEER = false>
 __global__ void __launch_bounds__(MAXT, MINB)
 spmm_stream_f32_kernel(const StreamParams p) {
     constexpr int RPW = 32 / LPR;                 // row groups (= rows in flight) per warp
@@ -348,8 +355,20 @@ spmm_stream_f32_kernel(const StreamParams p) {
     }
     if (BSRC != BSRC_GLOBAL) mbar_wait(bfull, 0);
 
+    const float inv_block = PEER ? 1.0f / (float)p.peer_block : 0.f;
     auto gather = [&](int c, int v) -> float4 {
-        if (BSRC == BSRC_GLOBAL) {
+        if (BSRC == BSRC_GLOBAL && PEER) {
+            // owner rank of row c: float estimate of c / block, corrected to the exact quotient
+            int r = (int)((float)c * inv_block);
+            int local = c - r * p.peer_block;
+            if (local < 0) { r--; local += p.peer_block; }
+            if (local >= p.peer_block) { r++; local -= p.peer_block; }
+            const char* base = p.peer_base[r] + (size_t)l * 16;
+            float4 out4;      // plain (coherent) load: peer memory is not read-only for the kernel's lifetime
+            const float4* ptr = reinterpret_cast<const float4*>(base + (size_t)(unsigned)local * rowbytes) + v * LPR;
+            asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(out4.x), "=f"(out4.y), "=f"(out4.z), "=f"(out4.w) : "l"(ptr));
+            return out4;
+        } else if (BSRC == BSRC_GLOBAL) {
             return __ldg(reinterpret_cast<const float4*>(bg_lane + (size_t)(unsigned)c * rowbytes) + v * LPR);
         } else {
             return *reinterpret_cast<const float4*>(bs_lane + (uint32_t)c * bs_rowbytes + v * (LPR * 16));
@@ -436,6 +455,7 @@ spmm_stream_f32_kernel(const StreamParams p) {
                 const int q = v * LPR + l;
                 if (EXACT || q < P4) {
                     float4 r = acc[v];
+                    if (p.accumulate) { const float4 o = orow[q]; r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
                     if (p.relu) r = relu4(r);     // val = (acc > 0 || relu == 0) ? acc : 0   (K:2586-2590)
                     if (p.streaming_store) __stcs(orow + q, r); else orow[q] = r;
                 }

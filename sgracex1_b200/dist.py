@@ -130,9 +130,187 @@ def abi_adj_fn(handle):
 
 
 # ------------------------------------------------------------------------------------------
+# peer-gather layer: no all-gather, the ADJ kernel reads remote rows over NVLink
+# ------------------------------------------------------------------------------------------
+class _RawCuda:
+    """A raw device pointer dressed up for torch.as_tensor (zero copy)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+
+
+class PeerGatherLayer:
+    """Row-partitioned layer whose ADJ stage gathers the partitioned operand straight from the
+    owning GPU (peer-mapped buffers, loads over NVLink) instead of all-gathering it first: only
+    the rows an adjacency row references cross the links.
+
+    order "agg_first" (dense X, M < P): the partitioned operand is X itself, the layer is
+        D_local = act((A_local . X) . W)              -- nothing is exchanged but the gathered rows
+    order "reference": FEA writes XW_local into the peer buffer, a barrier, then D_local = act(A_local . XW).
+    `exchange_handles(list_of_local_handles) -> list over ranks` abstracts the rendezvous
+    (torch.distributed.all_gather_object by default) so a single process can emulate several ranks."""
+
+    def __init__(self, handle, n_rows, width, rank, world, device, exchange=None):
+        self.h, self.N, self.width, self.rank, self.world = handle, n_rows, width, rank, world
+        self.block = row_block(n_rows, world)
+        self.lo, self.hi = row_range(n_rows, rank, world)
+        addr, ipc = handle.peer_alloc(self.block * width * 4)
+        self.addr = addr
+        if exchange is None:
+            def exchange(mine):
+                out = [None] * world
+                dist.all_gather_object(out, mine)
+                return out
+        handles = exchange(ipc) if world > 1 else [ipc]
+        self.bases = [addr if r == rank else handle.peer_open(handles[r]) for r in range(world)]
+        self.local = torch.as_tensor(_RawCuda(addr, (self.block, width)), device=device)
+        self.local.zero_()
+
+    def adj(self, adj_local, relu):
+        """act(A_local . M_all), M_all = the partitioned matrix (rows of rank r at bases[r])."""
+        from . import _lib
+        rp, ci, va = adj_local
+        n = rp.numel() - 1
+        out = torch.empty(n, self.width, dtype=torch.float32, device=rp.device)
+        d = _lib.LayerDesc()
+        d.N_adj, d.M_adj, d.P_w, d.relu = n, self.block * self.world, self.width, int(relu)
+        d.rowPtr_adj, d.columnIndex_adj, d.values_adj = rp.data_ptr(), ci.data_ptr(), va.data_ptr()
+        d.nnz_adj = int(ci.numel())
+        d.D = out.data_ptr()
+        self.h.adj_run_peer(d, self.bases, self.block)
+        return out
+
+    def forward_agg_first(self, adj_local, W, relu):
+        """X_local must already be in self.local[:hi-lo] and visible to the peers (barrier)."""
+        t = self.adj(adj_local, 0)
+        M, P = W.shape
+        Bt = W.t().contiguous()
+        out = torch.empty(t.shape[0], P, dtype=torch.float32, device=t.device)
+        self.h.dense_run(t.data_ptr(), Bt.data_ptr(), out.data_ptr(), t.shape[0], M, P, relu)
+        return out, (t, Bt)
+
+    def release(self):
+        self.h.peer_release()
+
+
+# ------------------------------------------------------------------------------------------
+# halo layer: gather exactly the remote rows the local adjacency references, overlapped with the
+# local part of the aggregation
+# ------------------------------------------------------------------------------------------
+def split_by_ownership(rowptr, col, val, lo, hi, block):
+    """Split a rank's adjacency rows (global column ids) into the part whose columns it owns and the
+    part it does not.  Returns (A_loc, A_rem, halo_rows): A_loc columns are local row indices
+    (col - lo); A_rem columns are block + position in `halo_rows` (the sorted unique remote ids), so
+    both index one buffer laid out as [block local rows | halo rows]."""
+    col = np.asarray(col)
+    n = len(rowptr) - 1
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(rowptr))
+    own = (col >= lo) & (col < hi)
+
+    def csr(mask, newcol):
+        rp = np.zeros(n + 1, np.int32)
+        np.cumsum(np.bincount(rows[mask], minlength=n), out=rp[1:])
+        return rp, newcol.astype(np.int32), np.asarray(val)[mask]
+
+    halo_rows, inv = np.unique(col[~own], return_inverse=True)
+    a_loc = csr(own, col[own].astype(np.int64) - lo)
+    a_rem = csr(~own, block + inv.astype(np.int64))
+    return a_loc, a_rem, halo_rows.astype(np.int32)
+
+
+class HaloLayer:
+    """D_local = act((A_local . X) . W) on a row-partitioned X (aggregate-first order, M < P).
+
+    Set-up (once per graph, host): the local adjacency is split by column ownership and the remote
+    column ids are renumbered into a halo.  Per layer: (1) the halo rows are copied from their owners
+    over NVLink by a thread-per-16-bytes kernel on a side stream, while (2) the main stream
+    aggregates the owned columns; (3) the remote part is added (accumulate pass), (4) the dense
+    stage runs on the tensor cores.  Only the rows actually referenced cross the links."""
+
+    def __init__(self, handle_main, handle_halo, adj_local_np, n_rows, width, rank, world, device, exchange=None):
+        import torch
+        self.hm, self.hh, self.N, self.width, self.rank, self.world = handle_main, handle_halo, n_rows, width, rank, world
+        self.block = row_block(n_rows, world)
+        self.lo, self.hi = row_range(n_rows, rank, world)
+        a_loc, a_rem, halo_rows = split_by_ownership(*adj_local_np, self.lo, self.hi, self.block)
+        self.n_halo = int(len(halo_rows))
+        self.nnz_remote = int(len(a_rem[1]))
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+        self.a_loc = tuple(up(a) for a in a_loc)
+        self.a_rem = tuple(up(a) for a in a_rem)
+        self.halo_rows = up(halo_rows)
+        addr, ipc = handle_main.peer_alloc((self.block + max(self.n_halo, 1)) * width * 4)
+        self.addr = addr
+        if exchange == "defer":          # single-process emulation of several ranks: the caller fills .bases
+            self.bases = None
+        else:
+            if exchange is None:
+                def exchange(mine):
+                    out = [None] * world
+                    dist.all_gather_object(out, mine)
+                    return out
+            handles = exchange(ipc) if world > 1 else [ipc]
+            self.bases = [addr if r == rank else handle_main.peer_open(handles[r]) for r in range(world)]
+        self.buf = torch.as_tensor(_RawCuda(addr, (self.block + max(self.n_halo, 1), width)), device=device)
+        self.buf.zero_()
+        self.local = self.buf[:self.block]          # this rank's rows of X go here
+        self.halo = self.buf[self.block:]
+        self.s_main = torch.cuda.current_stream(device)
+        self.s_halo = torch.cuda.Stream(device)
+        self.hh.set_stream(self.s_halo.cuda_stream)
+        self.ev_ready, self.ev_halo = torch.cuda.Event(), torch.cuda.Event()
+
+    def _adj(self, adj, out, accumulate):
+        from . import _lib
+        rp, ci, va = adj
+        n = rp.numel() - 1
+        d = _lib.LayerDesc()
+        d.N_adj, d.M_adj, d.P_w, d.relu = n, self.buf.shape[0], self.width, 0
+        d.rowPtr_adj, d.columnIndex_adj, d.values_adj = rp.data_ptr(), ci.data_ptr(), va.data_ptr()
+        d.nnz_adj = int(ci.numel())
+        d.D = out.data_ptr()
+        self.hm.set_option(_lib.OPT_ACCUMULATE, 1 if accumulate else 0)
+        try:
+            self.hm.adj_run(d, self.buf.data_ptr(), self.buf.shape[0])
+        finally:
+            self.hm.set_option(_lib.OPT_ACCUMULATE, 0)
+
+    def forward(self, W, relu):
+        """X_local must be in self.local and every rank must have reached this point (the caller's
+        barrier / token all-reduce on the main stream precedes this call)."""
+        import torch
+        n = self.hi - self.lo
+        t = torch.empty(n, self.width, dtype=torch.float32, device=self.buf.device)
+        self.ev_ready.record(self.s_main)
+        if self.n_halo:
+            self.s_halo.wait_event(self.ev_ready)
+            self.hh.halo_gather(self.bases, self.block, self.halo_rows.data_ptr(), self.n_halo, self.width, self.halo.data_ptr())
+            self.ev_halo.record(self.s_halo)
+        self._adj(self.a_loc, t, False)
+        if self.n_halo:
+            self.s_main.wait_event(self.ev_halo)
+            self._adj(self.a_rem, t, True)
+        M, P = W.shape
+        Bt = W.t().contiguous()
+        out = torch.empty(n, P, dtype=torch.float32, device=t.device)
+        self.hm.dense_run(t.data_ptr(), Bt.data_ptr(), out.data_ptr(), n, M, P, relu)
+        return out, (t, Bt)
+
+    def release(self):
+        self.hm.peer_release()
+
+
+# ------------------------------------------------------------------------------------------
 # bench.py --workload products
 # ------------------------------------------------------------------------------------------
 def bench_products(args):
+    """ogbn-products-shape dense layer, rows of X and A partitioned over the ranks (strong scaling).
+
+    --order agg_first (default): D = act((A.X).W), the opt-in order for M_fea < P_w; with several
+        ranks the ADJ kernel gathers the rows of X it needs from the owning GPU over NVLink
+        (PeerGatherLayer) -- no all-gather.
+    --order reference: D = act(A.(X.W)); with several ranks XW is all-gathered (NCCL) between the stages."""
     from . import _lib
     from . import graphs as G
 
@@ -144,6 +322,7 @@ def bench_products(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     scale = float(getattr(args, "scale", 1.0) or 1.0)
+    order = getattr(args, "order", "agg_first") or "agg_first"
     N = int(2_449_029 * scale)
     M, P = 100, 256
     lo, hi = row_range(N, rank, world)
@@ -160,27 +339,65 @@ def bench_products(args):
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     handle.set_stream(stream.cuda_stream)
-    layer = RowPartitionedLayer(N, P, rank, world, dev, abi_fea_fn(handle), abi_adj_fn(handle))
+    token = torch.zeros(1, device=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    exchanged = 0
+    if order == "agg_first" and world > 1:
+        handle2 = _lib.Handle(local)
+        handle2.set_option(_lib.OPT_MODE, _lib.MODE_F32_FAST)
+        handle2.set_option(_lib.OPT_STAGING, 0)
+        layer = HaloLayer(handle, handle2, (rp, ci, va), N, M, rank, world, dev)
+        layer.local[:hi - lo].copy_(x_local)
+        exchanged = int(layer.n_halo * M * 4)
+        barrier()
+
+        def step():
+            # every rank's X must be in place before anyone reads it: a one-element all-reduce on the stream
+            dist.all_reduce(token)
+            return layer.forward(W, 1)
+        mode = ("act((A.X).W); halo exchange: the remote rows of X the local adjacency references are copied over NVLink "
+                "from peer-mapped buffers while the owned columns are aggregated (no all-gather)")
+    elif order == "agg_first":
+        handle.set_option(_lib.OPT_AGG_FIRST, 1)
+        Bt = W.t().contiguous()
+        out = torch.empty(hi - lo, P, device=dev)
+        d = _lib.LayerDesc()
+        d.gemm_mode, d.relu, d.N_adj, d.M_adj, d.M_fea, d.P_w = 1, 1, N, N, M, P
+        d.values_fea, d.B, d.D = x_local.data_ptr(), Bt.data_ptr(), out.data_ptr()
+        d.rowPtr_adj, d.columnIndex_adj, d.values_adj = adj_local[0].data_ptr(), adj_local[1].data_ptr(), adj_local[2].data_ptr()
+        d.nnz_adj = int(adj_local[1].numel())
+
+        def step():
+            handle.layer_run(d)
+            return out
+        mode = "act((A.X).W) (opt-in aggregate-first order), one GPU"
+    else:
+        layer = RowPartitionedLayer(N, P, rank, world, dev, abi_fea_fn(handle), abi_adj_fn(handle))
+        exchanged = int(layer.block * (world - 1) * P * 4)
+
+        def step():
+            return layer.forward(x_local, W, adj_local, 1)
+        mode = "act(A.(X.W)), all-gather of XW between the stages"
+
     keep = None
     for _ in range(max(args.warmup, 3)):
-        keep = layer.forward(x_local, W, adj_local, 1)
+        keep = step()
     barrier()
     l0 = handle.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        keep = layer.forward(x_local, W, adj_local, 1)
+        keep = step()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
     launches = handle.launch_count() - l0
-    nnz_local = int(ci.numel() if hasattr(ci, "numel") else len(ci))
+    nnz_local = int(adj_local[1].numel())
     t = torch.tensor([ms, float(nnz_local)], dtype=torch.float64, device=dev)
     if world > 1:
         tm = t.clone()
@@ -197,12 +414,15 @@ def bench_products(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "products", "nodes": N, "nnz_adj": int(nnz_total), "features": M, "hidden": P,
-                       "mode": "dense gemm_mode layer, rows partitioned over the ranks, all-gather of XW between the stages",
-                       "l2": "XW 2.5 GB >> 126 MB L2, no flush needed", "graph_gen_s": gen_s},
+                       "order": order, "mode": "dense gemm_mode layer, rows partitioned over the ranks; " + mode,
+                       "l2": "X 0.98 GB / XW 2.5 GB >> 126 MB L2, no flush needed", "graph_gen_s": gen_s},
             "gpu_launches": int(launches),
             "layer_gbs": (fea_bytes + adj_bytes) / (ms * 1e-3) / 1e9,
-            "allgather_bytes_per_rank": int(layer.block * (world - 1) * P * 4),
+            "exchanged_bytes_per_rank": exchanged,
         }), flush=True)
     del keep
     if world > 1:
+        dist.barrier()
+        if order == "agg_first":
+            layer.release()
         dist.destroy_process_group()

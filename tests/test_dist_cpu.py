@@ -146,3 +146,29 @@ def test_partition_helpers():
         shards = [sdist.shard_graphs(n, r, w) for r in range(w)]
         assert shards[0][0] == 0 and shards[-1][1] == n
         assert max(b - a for a, b in shards) - min(b - a for a, b in shards) <= 1
+
+
+def test_split_by_ownership_reassembles_the_adjacency():
+    pr = U.random_problem(8, n=120, m=8, p=4, avg_deg=5)
+    rp, ci, va = pr["adj"]
+    world = 3
+    block = sdist.row_block(120, world)
+    x = np.random.default_rng(0).standard_normal((120, 8)).astype(np.float32)
+    A = np.zeros((120, 120), np.float32)
+    for r in range(120):
+        A[r, ci[rp[r]:rp[r + 1]]] = va[rp[r]:rp[r + 1]]
+    want = A @ x
+    for rank in range(world):
+        lo, hi = sdist.row_range(120, rank, world)
+        loc = sdist.csr_row_slice(rp, ci, va, lo, hi)
+        a_loc, a_rem, halo_rows = sdist.split_by_ownership(*loc, lo, hi, block)
+        assert np.all((halo_rows < lo) | (halo_rows >= hi)) and np.all(np.diff(halo_rows) > 0)
+        buf = np.zeros((block + len(halo_rows), 8), np.float32)
+        buf[:hi - lo] = x[lo:hi]
+        buf[block:] = x[halo_rows]
+        got = np.zeros((hi - lo, 8), np.float32)
+        for (r2, c2, v2) in (a_loc, a_rem):
+            assert len(r2) == hi - lo + 1
+            for r in range(hi - lo):
+                got[r] += v2[r2[r]:r2[r + 1]] @ buf[c2[r2[r]:r2[r + 1]]]
+        np.testing.assert_allclose(got, want[lo:hi], rtol=1e-5, atol=1e-6)

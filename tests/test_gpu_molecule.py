@@ -130,3 +130,91 @@ def test_row_partitioned_layer_world1_and_stage_split():
         part = sdist.abi_adj_fn(handle)(loc, xw, 1)
         handle.wait()
         U.assert_close_f32(part.cpu().numpy(), want.numpy()[lo:hi], what=f"rank {r} rows")
+
+
+def test_peer_gather_layer_two_emulated_ranks_on_one_gpu():
+    """The NVLink peer-gather ADJ with its row-partitioned operand split over two buffers of the same
+    GPU (what two ranks would map from each other): every rank's rows must equal the single-GPU layer."""
+    pr = U.random_problem(17, n=1501, m=100, p=256, avg_deg=6)
+    rp, ci, va = pr["adj"]
+    # one very long row so that the segmented long-row kernel runs with the peer table too
+    rng = np.random.default_rng(3)
+    deg = np.diff(rp).copy()
+    rows = [ci[rp[r]:rp[r + 1]] for r in range(1501)]
+    rows[700] = np.arange(1501, dtype=np.int32)
+    deg[700] = 1501
+    rp = np.zeros(1502, np.int32)
+    np.cumsum(deg, out=rp[1:])
+    ci = np.concatenate(rows).astype(np.int32)
+    va = rng.uniform(-0.2, 0.2, size=len(ci)).astype(np.float32)
+    dev = torch.device("cuda:0")
+    handle = _lib.Handle(0)
+    handle.set_option(_lib.OPT_STAGING, 0)
+    handle.set_option(_lib.OPT_MODE, _lib.MODE_F32_FAST)
+    x, W = pr["x"], pr["W"]
+    adj_c = (torch.from_numpy(rp), torch.from_numpy(ci), torch.from_numpy(va))
+    want = torch_adj(adj_c, torch.from_numpy(x @ W), 1).numpy()
+    world = 2
+    lay = sdist.PeerGatherLayer(handle, 1501, 100, 0, 1, dev)     # re-pointed at the two emulated ranks below
+    block = sdist.row_block(1501, world)
+    bufs = []
+    for r in range(world):
+        addr, _ = handle.peer_alloc(block * 100 * 4)
+        t = torch.as_tensor(sdist._RawCuda(addr, (block, 100)), device=dev)
+        lo, hi = sdist.row_range(1501, r, world)
+        t.zero_()
+        t[:hi - lo] = torch.from_numpy(x[lo:hi]).to(dev)
+        bufs.append((addr, t))
+    torch.cuda.synchronize()
+    Wd = torch.from_numpy(W).to(dev)
+    for r in range(world):
+        lo, hi = sdist.row_range(1501, r, world)
+        loc = tuple(torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in sdist.csr_row_slice(rp, ci, va, lo, hi))
+        lay.world, lay.block, lay.bases = world, block, [b[0] for b in bufs]
+        out, keep = lay.forward_agg_first(loc, Wd, 1)
+        handle.wait()
+        U.assert_close_f32(out.cpu().numpy(), want[lo:hi], what=f"peer-gather rank {r}")
+    handle.peer_release()
+
+
+def test_halo_layer_three_emulated_ranks_on_one_gpu():
+    """Halo exchange + split aggregation + tensor-core dense stage: every emulated rank's rows must
+    equal the single-GPU layer act(A (X W))."""
+    n, m, p = 3000, 100, 256
+    pr = U.random_problem(23, n=n, m=m, p=p, avg_deg=8)
+    rp, ci, va = pr["adj"]
+    rows = [ci[rp[r]:rp[r + 1]] for r in range(n)]
+    rows[1234] = np.arange(0, n, 2, dtype=np.int32)          # a hub row with many remote columns (long-row path)
+    deg = np.array([len(r) for r in rows])
+    rp = np.zeros(n + 1, np.int32)
+    np.cumsum(deg, out=rp[1:])
+    ci = np.concatenate(rows).astype(np.int32)
+    va = np.random.default_rng(5).uniform(-0.2, 0.2, size=len(ci)).astype(np.float32)
+    x, W = pr["x"], pr["W"]
+    adj_c = (torch.from_numpy(rp), torch.from_numpy(ci), torch.from_numpy(va))
+    want = torch_adj(adj_c, torch.from_numpy(x @ W), 1).numpy()
+    dev = torch.device("cuda:0")
+    world = 3
+    hm, hh = _lib.Handle(0), _lib.Handle(0)
+    for h in (hm, hh):
+        h.set_option(_lib.OPT_STAGING, 0)
+        h.set_option(_lib.OPT_MODE, _lib.MODE_F32_FAST)
+    hm.set_stream(torch.cuda.current_stream().cuda_stream or 1)
+    layers = []
+    for r in range(world):
+        lo, hi = sdist.row_range(n, r, world)
+        loc = sdist.csr_row_slice(rp, ci, va, lo, hi)
+        lay = sdist.HaloLayer(hm, hh, loc, n, m, r, world, dev, exchange="defer")
+        lay.local[:hi - lo].copy_(torch.from_numpy(x[lo:hi]).to(dev))
+        layers.append(lay)
+    for lay in layers:
+        lay.bases = [l2.addr for l2 in layers]
+    torch.cuda.synchronize()
+    Wd = torch.from_numpy(W).to(dev)
+    for r, lay in enumerate(layers):
+        out, keep = lay.forward(Wd, 1)
+        torch.cuda.synchronize()
+        lo, hi = sdist.row_range(n, r, world)
+        assert lay.n_halo > 0 and lay.nnz_remote > 0
+        U.assert_close_f32(out.cpu().numpy(), want[lo:hi], what=f"halo layer rank {r}")
+    hm.peer_release()

@@ -1,4 +1,2 @@
 exec > gpurun_out/run3.log 2>&1
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python tools/products_breakdown.py 1.0 2>&1 | grep -v Warn | grep -v "ref = "
-python bench.py --steps 20 --warmup 3 --no-cpu 2>&1 | python tools/brief.py
+python -m pytest tests/test_gpu_molecule.py -m gpu -x -q -k "halo or peer" 2>&1 | grep -E "^E|Error|error|passed|failed" | head -12
