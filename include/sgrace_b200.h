@@ -207,6 +207,11 @@ int sgrace_adj_run_peer(sgrace_handle* h, const sgrace_layer_desc* d, const uint
  * float32 matrix (`width` floats per row, multiple of 4) from their owners into `dst` (device) */
 int sgrace_halo_gather(sgrace_handle* h, const uint64_t* bases, int32_t n_peers, int32_t block_rows, const int32_t* rows,
                        int64_t n_rows, int32_t width, void* dst);
+/* the same exchange pushed by the owner: for each of n_dst destinations, rows_ptrs[d] (device int32
+ * array of counts[d] LOCAL row indices) are copied from `local` to dst_ptrs[d] (peer-mapped address of
+ * the destination's first halo slot for this owner), in order */
+int sgrace_halo_push(sgrace_handle* h, const void* local, int32_t width, int32_t n_dst, const uint64_t* rows_ptrs,
+                     const int64_t* counts, const uint64_t* dst_ptrs);
 
 /* number of this library's kernels launched on the handle since creation (bench evidence) */
 int sgrace_launch_count(sgrace_handle* h, uint64_t* count);

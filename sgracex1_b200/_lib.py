@@ -24,7 +24,7 @@ EXPORTS = (
     "sgrace_get_option", "sgrace_set_stream", "sgrace_start", "sgrace_done", "sgrace_wait",
     "sgrace_stage_times", "sgrace_layer_run", "sgrace_fea_run", "sgrace_adj_run",
     "sgrace_launch_count", "sgrace_dense_run", "sgrace_peer_alloc", "sgrace_peer_open", "sgrace_peer_release",
-    "sgrace_adj_run_peer", "sgrace_halo_gather",
+    "sgrace_adj_run_peer", "sgrace_halo_gather", "sgrace_halo_push",
 )
 
 
@@ -94,6 +94,7 @@ def load():
     lib.sgrace_peer_release.argtypes = [H]
     lib.sgrace_adj_run_peer.argtypes = [H, C.POINTER(LayerDesc), C.POINTER(C.c_uint64), C.c_int32, C.c_int32]
     lib.sgrace_halo_gather.argtypes = [H, C.POINTER(C.c_uint64), C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
+    lib.sgrace_halo_push.argtypes = [H, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_int64), C.POINTER(C.c_uint64)]
     lib.sgrace_dense_run.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     for name in EXPORTS:
         if name not in ("sgrace_last_error", "sgrace_version"):
@@ -233,6 +234,11 @@ class Handle:
         arr = (C.c_uint64 * len(bases))(*[int(b) for b in bases])
         self._ck(self.lib.sgrace_halo_gather(self.h, arr, len(bases), int(block_rows), C.c_void_p(rows_ptr), int(n_rows),
                                              int(width), C.c_void_p(dst_ptr)))
+
+    def halo_push(self, local_ptr, width, rows_ptrs, counts, dst_ptrs):
+        n = len(rows_ptrs)
+        self._ck(self.lib.sgrace_halo_push(self.h, C.c_void_p(local_ptr), int(width), n, (C.c_uint64 * n)(*[int(p) for p in rows_ptrs]),
+                                           (C.c_int64 * n)(*[int(c) for c in counts]), (C.c_uint64 * n)(*[int(p) for p in dst_ptrs])))
 
     def launch_count(self):
         v = C.c_uint64()

@@ -1086,6 +1086,37 @@ int sgrace_halo_gather(sgrace_handle* h, const uint64_t* bases, int32_t n_peers,
     return SGRACE_OK;
 }
 
+int sgrace_halo_push(sgrace_handle* h, const void* local, int32_t width, int32_t n_dst, const uint64_t* rows_ptrs,
+                     const int64_t* counts, const uint64_t* dst_ptrs) {
+    if (!h) return SGRACE_EINVAL;
+    h->last_status = 0;
+    CU(cudaSetDevice(h->device));
+    if (!local || width < 4 || width % 4 || n_dst < 0 || n_dst > 8 || (n_dst && (!rows_ptrs || !counts || !dst_ptrs)))
+        return fail(h, SGRACE_EINVAL, "bad halo-push argument");
+    PushTable pt;
+    memset(&pt, 0, sizeof(pt));
+    pt.count = n_dst;
+    long long total_rows = 0;
+    for (int d = 0; d < n_dst; d++) {
+        if (counts[d] < 0) return fail(h, SGRACE_EINVAL, "negative halo-push count");
+        pt.rows[d] = (const int*)(uintptr_t)rows_ptrs[d];
+        pt.dst[d] = (float4*)(uintptr_t)dst_ptrs[d];
+        pt.start[d] = total_rows;
+        total_rows += counts[d];
+    }
+    pt.start[n_dst] = total_rows;
+    if (total_rows == 0) return SGRACE_OK;
+    const size_t smem = (size_t)2 * HALO_CHUNK * width * 4;
+    if (smem > 200 * 1024) return fail(h, SGRACE_EUNSUPPORTED, "halo push: rows wider than 400 floats are not supported");
+    CU(cudaFuncSetAttribute(halo_push_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long grid = total_rows / HALO_CHUNK + n_dst;
+    if (grid > (long long)h->num_sms * 4) grid = (long long)h->num_sms * 4;
+    halo_push_kernel<<<(int)grid, 256, smem, h->stream>>>(pt, (const float4*)local, width / 4);
+    h->launches++;
+    CU(cudaGetLastError());
+    return SGRACE_OK;
+}
+
 int sgrace_adj_run_peer(sgrace_handle* h, const sgrace_layer_desc* d, const uint64_t* bases, int32_t n_peers,
                         int32_t block_rows) {
     if (!h) return SGRACE_EINVAL;

@@ -219,6 +219,14 @@ def split_by_ownership(rowptr, col, val, lo, hi, block):
     return a_loc, a_rem, halo_rows.astype(np.int32)
 
 
+def renumber_columns(rowptr, col, val, lo, hi, block, halo_rows):
+    """The unsplit adjacency with columns renumbered into the [block local rows | halo rows] buffer."""
+    col = np.asarray(col).astype(np.int64)
+    own = (col >= lo) & (col < hi)
+    new = np.where(own, col - lo, block + np.searchsorted(halo_rows, col))
+    return np.asarray(rowptr, np.int32), new.astype(np.int32), np.asarray(val)
+
+
 class HaloLayer:
     """D_local = act((A_local . X) . W) on a row-partitioned X (aggregate-first order, M < P).
 
@@ -239,6 +247,11 @@ class HaloLayer:
         up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
         self.a_loc = tuple(up(a) for a in a_loc)
         self.a_rem = tuple(up(a) for a in a_rem)
+        self.a_all = tuple(up(a) for a in renumber_columns(*adj_local_np, self.lo, self.hi, self.block, halo_rows))
+        # overlap = aggregate the owned columns while the halo travels, then add the remote part; the default
+        # runs the exchange first and one aggregation pass after it: with a persistent kernel holding every SM
+        # the concurrent exchange (and its NCCL completion signal) is starved until that kernel drains
+        self.overlap = bool(os.environ.get("SGRACE_HALO_OVERLAP"))
         self.halo_rows = up(halo_rows)
         addr, ipc = handle_main.peer_alloc((self.block + max(self.n_halo, 1)) * width * 4)
         self.addr = addr
@@ -256,10 +269,47 @@ class HaloLayer:
         self.buf.zero_()
         self.local = self.buf[:self.block]          # this rank's rows of X go here
         self.halo = self.buf[self.block:]
+        # push lists: which of MY rows every other rank needs, and where they go in its halo
+        self.push = None
+        if exchange != "defer" and world > 1:
+            self._exchange_push_lists(halo_rows, device)
         self.s_main = torch.cuda.current_stream(device)
         self.s_halo = torch.cuda.Stream(device)
         self.hh.set_stream(self.s_halo.cuda_stream)
         self.ev_ready, self.ev_halo = torch.cuda.Event(), torch.cuda.Event()
+        self._token = torch.zeros(1, device=device)
+
+    def _exchange_push_lists(self, halo_rows, device, gather=None):
+        """halo_rows is sorted, so the rows wanted from owner o are one contiguous run of halo slots."""
+        import torch
+        bounds = np.searchsorted(halo_rows, [o * self.block for o in range(self.world + 1)])
+        want = {o: (int(bounds[o]), halo_rows[bounds[o]:bounds[o + 1]]) for o in range(self.world) if o != self.rank}
+        if gather is None:
+            allw = [None] * self.world
+            dist.all_gather_object(allw, want)
+        else:
+            allw = gather(want)
+        rows_t, counts, dsts = [], [], []
+        for r in range(self.world):
+            if r == self.rank or self.rank not in allw[r]:
+                continue
+            slot0, rows = allw[r][self.rank]
+            if len(rows) == 0:
+                continue
+            rows_t.append(torch.from_numpy(np.ascontiguousarray(rows.astype(np.int64) - self.lo).astype(np.int32)).to(device))
+            counts.append(len(rows))
+            dsts.append(self.bases[r] + (self.block + slot0) * self.width * 4)
+        self.push = (rows_t, counts, dsts)
+        # the same exchange through NCCL all-to-all: pack locally, one all_to_all_single into the halo region
+        send_counts = [0] * self.world
+        k = 0
+        for r in range(self.world):
+            if r != self.rank and self.rank in allw[r] and len(allw[r][self.rank][1]):
+                send_counts[r] = counts[k]
+                k += 1
+        recv_counts = [int(bounds[o + 1] - bounds[o]) if o != self.rank else 0 for o in range(self.world)]
+        self.a2a = dict(send=torch.empty(max(sum(send_counts), 1), self.width, dtype=torch.float32, device=device),
+                        in_splits=send_counts, out_splits=recv_counts)
 
     def _adj(self, adj, out, accumulate):
         from . import _lib
@@ -276,25 +326,63 @@ class HaloLayer:
         finally:
             self.hm.set_option(_lib.OPT_ACCUMULATE, 0)
 
-    def forward(self, W, relu):
+    def forward(self, W, relu, timing=None):
         """X_local must be in self.local and every rank must have reached this point (the caller's
-        barrier / token all-reduce on the main stream precedes this call)."""
+        barrier / token all-reduce on the main stream precedes this call).  `timing`: optional dict that
+        receives per-phase milliseconds (synchronises; for diagnosis only)."""
         import torch
         n = self.hi - self.lo
         t = torch.empty(n, self.width, dtype=torch.float32, device=self.buf.device)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)] if timing is not None else None
         self.ev_ready.record(self.s_main)
-        if self.n_halo:
+        if self.n_halo or self.push is not None:
             self.s_halo.wait_event(self.ev_ready)
-            self.hh.halo_gather(self.bases, self.block, self.halo_rows.data_ptr(), self.n_halo, self.width, self.halo.data_ptr())
+            if ev: ev[4].record(self.s_halo)
+            mode = os.environ.get("SGRACE_HALO_EXCHANGE", "a2a")      # a2a | push | pull
+            if self.push is not None and mode == "a2a":
+                # pack the rows every destination wants (our kernel), one NCCL all-to-all straight into the halo
+                # region: measured 0.69 ms for 237 MB per rank on 8 GPUs, against 0.85 ms for bulk-store pushes
+                # and 1.2 ms for 16-byte pulls
+                rows_t, counts, _ = self.push
+                sb = self.a2a["send"]
+                offs = np.concatenate([[0], np.cumsum(counts)])[:-1]
+                self.hh.halo_push(self.local.data_ptr(), self.width, [t_.data_ptr() for t_ in rows_t], counts,
+                                  [sb.data_ptr() + int(o) * self.width * 4 for o in offs])
+                with torch.cuda.stream(self.s_halo):
+                    dist.all_to_all_single(self.halo[:self.n_halo], sb[:sum(counts)], self.a2a["out_splits"], self.a2a["in_splits"])
+            elif self.push is not None and mode == "push":
+                # owner pushes; a one-element all-reduce on the halo stream tells everyone the pushes have landed
+                rows_t, counts, dsts = self.push
+                self.hh.halo_push(self.local.data_ptr(), self.width, [t_.data_ptr() for t_ in rows_t], counts, dsts)
+                with torch.cuda.stream(self.s_halo):
+                    dist.all_reduce(self._token)
+            elif self.n_halo:
+                self.hh.halo_gather(self.bases, self.block, self.halo_rows.data_ptr(), self.n_halo, self.width, self.halo.data_ptr())
+            if ev: ev[5].record(self.s_halo)
             self.ev_halo.record(self.s_halo)
-        self._adj(self.a_loc, t, False)
-        if self.n_halo:
-            self.s_main.wait_event(self.ev_halo)
-            self._adj(self.a_rem, t, True)
+        if ev: ev[0].record(self.s_main)
+        if self.overlap:
+            self._adj(self.a_loc, t, False)
+            if ev: ev[1].record(self.s_main)
+            if self.n_halo:
+                self.s_main.wait_event(self.ev_halo)
+                self._adj(self.a_rem, t, True)
+        else:
+            if self.n_halo or self.push is not None:
+                self.s_main.wait_event(self.ev_halo)
+            if ev: ev[1].record(self.s_main)
+            self._adj(self.a_all, t, False)
+        if ev: ev[2].record(self.s_main)
         M, P = W.shape
         Bt = W.t().contiguous()
         out = torch.empty(n, P, dtype=torch.float32, device=t.device)
         self.hm.dense_run(t.data_ptr(), Bt.data_ptr(), out.data_ptr(), n, M, P, relu)
+        if ev:
+            ev[3].record(self.s_main)
+            torch.cuda.synchronize()
+            timing.update(adj_owned_ms=ev[0].elapsed_time(ev[1]), wait_halo_plus_adj_remote_ms=ev[1].elapsed_time(ev[2]),
+                          dense_ms=ev[2].elapsed_time(ev[3]), halo_gather_ms=ev[4].elapsed_time(ev[5]) if self.n_halo else 0.0,
+                          halo_rows=self.n_halo, halo_mb=self.n_halo * self.width * 4 / 1e6, nnz_remote=self.nnz_remote)
         return out, (t, Bt)
 
     def release(self):
@@ -388,6 +476,13 @@ def bench_products(args):
     for _ in range(max(args.warmup, 3)):
         keep = step()
     barrier()
+    if order == "agg_first" and world > 1 and os.environ.get("SGRACE_HALO_TIMING"):
+        tm = {}
+        dist.all_reduce(token)
+        layer.forward(W, 1, timing=tm)
+        print(f"[rank {rank}] halo layer phases: " + json.dumps({k: (round(v, 3) if isinstance(v, float) else v) for k, v in tm.items()}),
+              flush=True)
+        barrier()
     l0 = handle.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
