@@ -280,7 +280,7 @@ int launch_spmm_stream(sgrace_handle* h, const int* rp, const int* ci, const flo
     do {                                                                                                       \
         auto kern = spmm_stream_f32_kernel<LPR, NV, BS, MT, MB, EX>;                                           \
         int threads = env_int(BS == BSRC_GLOBAL ? "SGRACE_STREAM_THREADS_G" : "SGRACE_STREAM_THREADS_S",       \
-                              (BS == BSRC_GLOBAL && MT > 384) ? 384 : MT);                                     \
+                              (BS == BSRC_GLOBAL && MT > 384 && MT < 1024) ? 384 : MT);                        \
         if (threads > MT) threads = MT;                                                                        \
         threads = (threads / (32 * G)) * (32 * G);                                                             \
         if (threads < 64 * G) threads = 64 * G;                                                                \
@@ -293,7 +293,7 @@ int launch_spmm_stream(sgrace_handle* h, const int* rp, const int* ci, const flo
         const long long tiles = ((long long)nrows + TR - 1) / TR;                                              \
         long long grid = (long long)h->num_sms * per_sm;                                                       \
         if (grid > tiles) grid = tiles;                                                                        \
-        sp.static_tiles = (int)(tiles * static_pct / 100 / grid);                                              \
+        sp.static_tiles = (int)(tiles * static_pct / 100 / (grid * G));                                        \
         kern<<<(int)grid, threads, smem, h->stream>>>(sp);                                                     \
     } while (0)
     // register budgets: NV == 1 kernels fit 64 registers -> 1024-thread CTAs (smem gathers) or
@@ -326,6 +326,9 @@ int launch_spmm_stream(sgrace_handle* h, const int* rp, const int* ci, const flo
         } while (0)
         if (LPR == 32) { if (exact) STREAM_LAUNCH_PEER(512, MB_GLOB, true); else STREAM_LAUNCH_PEER(512, 1, false); }
 #undef STREAM_LAUNCH_PEER
+    } else if (exact && NV == 1 && env_int("SGRACE_STREAM_BIGG", 0)) {
+        // experiment: one 1024-thread CTA per SM walking a contiguous row range, L1 left to the gathered rows
+        if (NV == 1) STREAM_LAUNCH(BSRC_GLOBAL, 1024, 1, true);
     } else {
         if (exact) STREAM_LAUNCH(BSRC_GLOBAL, 512, MB_GLOB, true); else STREAM_LAUNCH(BSRC_GLOBAL, 512, 1, false);
     }

@@ -259,7 +259,7 @@ spmm_stream_f32_kernel(const StreamParams p) {
         const int static_total = p.static_tiles * (int)gridDim.x * G;
         auto claim = [&]() -> int {
             int t = 0;
-            if (seq < p.static_tiles) t = ((int)blockIdx.x * G + grp) * p.static_tiles + seq;
+            if (seq < p.static_tiles) t = (int)blockIdx.x * (G * p.static_tiles) + seq * G + grp;   // groups of a CTA interleave
             else if (lane == 0) t = static_total + atomicAdd(p.tile_counter, 1);
             seq++;
             return t;                               // valid in lane 0 only until shuffled
