@@ -1,2 +1,3 @@
-exec > gpurun_out/run3.log 2>&1
-python -m pytest tests/test_gpu_configs.py -m gpu -x -q 2>&1 | grep -E "^E|passed|failed|Error" | head -20
+exec > gpurun_out/sanitizer_r1.log 2>&1
+compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "fast_float_widths or edge_cases or long_rows or tensor_core" 2>&1 | tail -12
+echo "exit=$?"
