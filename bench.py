@@ -109,9 +109,9 @@ def dist_env():
     return rank, world, local
 
 
-def make_cora_batch(copies, seed0, unique=16):
+def make_cora_batch(copies, seed0, unique=16, P=16):
     from sgracex1_b200 import graphs as G
-    probs = [G.cora_shape(seed=seed0 + s) for s in range(min(unique, copies))]
+    probs = [G.cora_shape(seed=seed0 + s, P=P) for s in range(min(unique, copies))]
     return G.block_diagonal(probs, copies), probs
 
 
@@ -157,7 +157,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    _, probs = make_cora_batch(16, 0)
+    _, probs = make_cora_batch(16, 0, P=args.hidden or 16)
     nnz = float(np.mean([p.nnz_adj for p in probs]))
     # bounded sample: calibrate so the whole --steps/--warmup run takes well under a few minutes
     run, kind = cpu_layer_runner(probs)
@@ -173,8 +173,8 @@ def run_reference(args):
         "impl": "reference", "metric": "spmm_aggregated_gteps", "value": value, "unit": "GTEPS",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cora_x1024", "graphs_per_step": per_step, "nodes": 2708, "features": 1433,
-                   "hidden": 16, "mode": "sparse-feature GCN layer, ReLU"},
+        "config": {"workload": f"cora_x{args.copies}", "graphs_per_step": per_step, "nodes": 2708, "features": 1433,
+                   "hidden": args.hidden or 16, "mode": "sparse-feature GCN layer, ReLU"},
         "cpu_baseline": {"value": value, "unit": "GTEPS", "cores": threads, "kind": kind,
                          "sample": f"{per_step} Cora-shape layers per step ({per_step}/{args.copies} of the workload), "
                                    f"{'reference HLS source compiled natively (oracle/_ref, float build)' if kind == 'reference' else 'oracle port'}"},
@@ -205,7 +205,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     hbm_peak, _, peak_kind = measured_peaks()
-    batch, probs = make_cora_batch(args.copies, seed0=1000 * rank)
+    batch, probs = make_cora_batch(args.copies, seed0=1000 * rank, P=args.hidden or 16)
     ip = MmultTop(local)
     ip.configure(mode=_lib.MODE_F32_FAST, index_format=0, staging=0)
     stream = torch.cuda.Stream()          # kernels, copies and the timing events share this stream
@@ -295,7 +295,7 @@ def run_ours(args):
             "metric": "spmm_aggregated_gteps", "value": value, "unit": "GTEPS", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cora_x1024", "graphs_per_step_per_gpu": args.copies, "nodes": batch.N,
+            "config": {"workload": f"cora_x{args.copies}", "graphs_per_step_per_gpu": args.copies, "nodes": batch.N,
                        "features": batch.M, "hidden": batch.P, "nnz_adj": batch.nnz_adj, "nnz_fea": batch.nnz_fea,
                        "mode": "sparse-feature GCN layer, ReLU, SGRACE_MODE_F32_FAST",
                        "l2": f"inputs {ab['layer'] / 1e6:.0f} MB per step > 126 MB L2, no flush needed"},
@@ -344,7 +344,7 @@ def main():
     ap.add_argument("--copies", type=int, default=1024, help="Cora-shape graphs per step per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--graphs", type=int, default=0, help="molecule workload: graphs per step per GPU (default 188*64)")
-    ap.add_argument("--hidden", type=int, default=0, help="molecule workload: hidden width (default 64)")
+    ap.add_argument("--hidden", type=int, default=0, help="hidden width (cora: default 16, the BASELINE config; molecule: default 64)")
     ap.add_argument("--scale", type=float, default=1.0, help="products workload: fraction of the 2.45M-node shape")
     ap.add_argument("--order", default="agg_first", choices=["agg_first", "reference"],
                     help="products workload: act((A.X).W) (opt-in order, peer gathers over NVLink) or act(A.(X.W)) (all-gather)")

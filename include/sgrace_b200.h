@@ -213,6 +213,10 @@ int sgrace_halo_gather(sgrace_handle* h, const uint64_t* bases, int32_t n_peers,
 int sgrace_halo_push(sgrace_handle* h, const void* local, int32_t width, int32_t n_dst, const uint64_t* rows_ptrs,
                      const int64_t* counts, const uint64_t* dst_ptrs);
 
+/* saved-tensor backward helper of the notebook layer (FPYNQ.backward: grad_W = X^T (A g)):
+ * out[M x P] = X^T . Y for X [N x M], Y [N x P] row-major float32, N >> M, P; deterministic */
+int sgrace_xty_run(sgrace_handle* h, const void* X, const void* Y, void* out, int32_t N, int32_t M, int32_t P);
+
 /* number of this library's kernels launched on the handle since creation (bench evidence) */
 int sgrace_launch_count(sgrace_handle* h, uint64_t* count);
 

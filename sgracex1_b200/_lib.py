@@ -24,7 +24,7 @@ EXPORTS = (
     "sgrace_get_option", "sgrace_set_stream", "sgrace_start", "sgrace_done", "sgrace_wait",
     "sgrace_stage_times", "sgrace_layer_run", "sgrace_fea_run", "sgrace_adj_run",
     "sgrace_launch_count", "sgrace_dense_run", "sgrace_peer_alloc", "sgrace_peer_open", "sgrace_peer_release",
-    "sgrace_adj_run_peer", "sgrace_halo_gather", "sgrace_halo_push",
+    "sgrace_adj_run_peer", "sgrace_halo_gather", "sgrace_halo_push", "sgrace_xty_run",
 )
 
 
@@ -95,6 +95,7 @@ def load():
     lib.sgrace_adj_run_peer.argtypes = [H, C.POINTER(LayerDesc), C.POINTER(C.c_uint64), C.c_int32, C.c_int32]
     lib.sgrace_halo_gather.argtypes = [H, C.POINTER(C.c_uint64), C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     lib.sgrace_halo_push.argtypes = [H, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_int64), C.POINTER(C.c_uint64)]
+    lib.sgrace_xty_run.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
     lib.sgrace_dense_run.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     for name in EXPORTS:
         if name not in ("sgrace_last_error", "sgrace_version"):
@@ -239,6 +240,9 @@ class Handle:
         n = len(rows_ptrs)
         self._ck(self.lib.sgrace_halo_push(self.h, C.c_void_p(local_ptr), int(width), n, (C.c_uint64 * n)(*[int(p) for p in rows_ptrs]),
                                            (C.c_int64 * n)(*[int(c) for c in counts]), (C.c_uint64 * n)(*[int(p) for p in dst_ptrs])))
+
+    def xty_run(self, x_ptr, y_ptr, out_ptr, N, M, P):
+        self._ck(self.lib.sgrace_xty_run(self.h, C.c_void_p(x_ptr), C.c_void_p(y_ptr), C.c_void_p(out_ptr), int(N), int(M), int(P)))
 
     def launch_count(self):
         v = C.c_uint64()

@@ -242,6 +242,7 @@ int launch_spmm_stream(sgrace_handle* h, const int* rp, const int* ci, const flo
         }
     }
     C = env_int("SGRACE_STREAM_C", C) & ~3;
+    if (bsrc == BSRC_GLOBAL) C = env_int("SGRACE_STREAM_C_G", C) & ~3;
     G = env_int(bsrc == BSRC_GLOBAL ? "SGRACE_STREAM_G_G" : "SGRACE_STREAM_G_S", G);
     if (G < 1) G = 1;
     // stage geometry.  smem gathers: a claimed tile holds ~2.5 stages of non-zeros and is cut into
@@ -254,6 +255,7 @@ int launch_spmm_stream(sgrace_handle* h, const int* rp, const int* ci, const flo
     if (TR < 64) TR = 64;
     if (TR > (bsrc == BSRC_GLOBAL ? 512 : 1024)) TR = bsrc == BSRC_GLOBAL ? 512 : 1024;
     TR = env_int("SGRACE_STREAM_TR", TR);
+    if (bsrc == BSRC_GLOBAL) TR = env_int("SGRACE_STREAM_TR_G", TR);
     sp.tile_rows = TR; sp.stage_nnz = C; sp.groups = G;
 
     sp.b_bytes = bsrc == BSRC_SMEM_DUP ? (int)(2 * b_plain) : bsrc == BSRC_SMEM ? (int)b_plain : 0;
@@ -276,6 +278,8 @@ int launch_spmm_stream(sgrace_handle* h, const int* rp, const int* ci, const flo
     sp.dry_run = env_int("SGRACE_STREAM_DRY", 0);
     sp.l1_prefetch = bsrc == BSRC_GLOBAL ? env_int("SGRACE_STREAM_PF", 0) : 0;
     sp.prefetch_rows = (bsrc == BSRC_GLOBAL && env_int("SGRACE_STREAM_PREFETCH", 0)) ? b_total_rows : 0;
+    sp.prefetch_lead = env_int("SGRACE_STREAM_LEAD", 4096);
+    sp.reverse = (bsrc == BSRC_GLOBAL && final_out) ? env_int("SGRACE_STREAM_REVERSE", 0) : 0;
 #define STREAM_LAUNCH(BS, MT, MB, EX)                                                                          \
     do {                                                                                                       \
         auto kern = spmm_stream_f32_kernel<LPR, NV, BS, MT, MB, EX>;                                           \
@@ -1135,6 +1139,27 @@ int sgrace_adj_run_peer(sgrace_handle* h, const sgrace_layer_desc* d, const uint
     const int rc = run_adj(h, d, rp_adj, (const void*)(uintptr_t)bases[0], n_peers * block_rows);
     h->peer_count = 0;
     return rc;
+}
+
+int sgrace_xty_run(sgrace_handle* h, const void* X, const void* Y, void* out, int32_t N, int32_t M, int32_t P) {
+    if (!h) return SGRACE_EINVAL;
+    h->last_status = 0;
+    CU(cudaSetDevice(h->device));
+    if (!X || !Y || !out || N < 0 || M <= 0 || P <= 0) return fail(h, SGRACE_EINVAL, "bad argument");
+    const int tiles = ((M + 63) / 64) * ((P + 63) / 64);
+    int chunks = h->num_sms * 2 / tiles;
+    if (chunks < 1) chunks = 1;
+    int rows_per = (N + chunks - 1) / chunks;
+    rows_per = ((rows_per + 31) / 32) * 32;
+    if (rows_per < 32) rows_per = 32;
+    chunks = N > 0 ? (N + rows_per - 1) / rows_per : 1;
+    if (int rc = ensure(h, h->long_partial, sizeof(float) * 4096 * (size_t)chunks * tiles)) return rc;
+    xty_partial_kernel<<<dim3(chunks, tiles), 256, 0, h->stream>>>((const float*)X, (const float*)Y, (float*)h->long_partial.p, N, M,
+                                                                    P, rows_per);
+    xty_reduce_kernel<<<dim3(tiles, 16), 256, 0, h->stream>>>((const float*)h->long_partial.p, (float*)out, M, P, chunks, tiles);
+    h->launches += 2;
+    CU(cudaGetLastError());
+    return SGRACE_OK;
 }
 
 int sgrace_start(sgrace_handle* h) {

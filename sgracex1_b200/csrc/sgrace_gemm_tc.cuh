@@ -9,7 +9,7 @@
 //
 // Layouts need no transposition: X is [rows][K] K-major and the B buffer holds W transposed,
 // [P][K] K-major (kernelMatrixmult_all.cpp:3038-3051) -- exactly the two K-major operands of
-// tcgen05.mma.  One CTA owns a 128-column slice of W for the whole launch (hi and lo images resident
+// tcgen05.mma.  One CTA owns a 128-column (or 64-column) slice of W for the whole launch (hi and lo images resident
 // in shared memory) and walks 128-row tiles of X:
 //   warp 0      one lane: tcgen05.mma issuer
 //   warp 1      TMEM allocation
@@ -33,7 +33,6 @@ namespace sgrace {
 namespace tc {
 
 constexpr int BM = 128;          // rows per tile (UMMA M)
-constexpr int BN = 128;          // columns per CTA (UMMA N)
 constexpr int MAX_RING = 8;      // K-chunks in flight (as many as fit beside the resident W slice)
 constexpr int THREADS = 384;
 
@@ -48,8 +47,8 @@ struct Ctrl {
 constexpr int CTRL_BYTES = 1024;
 constexpr int STAGE_BYTES = 4 * 4096;
 
-inline size_t smem_bytes(int bk, int kc, int ring) {
-    return 1024 + CTRL_BYTES + STAGE_BYTES + (size_t)2 * kc * (BN * bk * 4) + (size_t)2 * ring * (BM * bk * 4);
+inline size_t smem_bytes(int bn, int bk, int kc, int ring) {
+    return 1024 + CTRL_BYTES + STAGE_BYTES + (size_t)2 * kc * (bn * bk * 4) + (size_t)2 * ring * (BM * bk * 4);
 }
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -114,7 +113,8 @@ __device__ __forceinline__ void split4(float4 v, float4& hi, float4& lo) {
     hi.w = tf32_hi(v.w); lo.w = v.w - hi.w;
 }
 
-template <int BK>
+// BN = columns of W per CTA (UMMA N): 128, or 64 for hidden widths that are only a multiple of 64
+template <int BK, int BN>
 __global__ void __launch_bounds__(THREADS, 1)
 fea_dense_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_o, int K, int P, int tiles, int ctas_per_slice, int kc, int ring,
@@ -306,7 +306,7 @@ inline int make_map(CUtensorMap* map, const float* base, int rows, int cols, int
 
 // X: N x M row-major; B: W transposed, P x M row-major; out: N x P row-major
 inline bool fea_dense_tc_supported(int N, int M, int P) {
-    return N >= tc::BM && M % 4 == 0 && M >= 32 && M <= 128 && P % tc::BN == 0 && P >= tc::BN;
+    return N >= tc::BM && M % 4 == 0 && M >= 32 && M <= 128 && P % 64 == 0 && P >= 64;
 }
 
 // returns 0 on success, -100 when the shape / pointers are not eligible (caller falls back), other
@@ -318,11 +318,12 @@ inline int fea_dense_tc_launch(const float* X, const float* B, float* out, int N
     int max_optin = 0, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const int bn = P % 128 == 0 ? 128 : 64;
     // chunk width: 32 floats (128-byte swizzle) unless 16 floats lets at least a whole tile of X be in flight
     auto ring_for = [&](int bk) {
         const int kc = (M + bk - 1) / bk;
         int ring = tc::MAX_RING;
-        while (ring > 1 && tc::smem_bytes(bk, kc, ring) > (size_t)max_optin) ring--;
+        while (ring > 1 && tc::smem_bytes(bn, bk, kc, ring) > (size_t)max_optin) ring--;
         return ring;
     };
     int bk = 32;
@@ -331,22 +332,28 @@ inline int fea_dense_tc_launch(const float* X, const float* B, float* out, int N
     const int kc = (M + bk - 1) / bk, ring = ring_for(bk);
     if (ring < 2) return -100;
     CUtensorMap mx, mb, mo;
-    if (tc::make_map(&mx, X, N, M, tc::BM, bk) != 0 || tc::make_map(&mb, B, P, M, tc::BN, bk) != 0 ||
+    if (tc::make_map(&mx, X, N, M, tc::BM, bk) != 0 || tc::make_map(&mb, B, P, M, bn, bk) != 0 ||
         tc::make_map(&mo, out, N, P, 32, 32) != 0)
         return -100;
     const int tiles = (N + tc::BM - 1) / tc::BM;
-    const int nslice = P / tc::BN;
+    const int nslice = P / bn;
     int per_slice = num_sms / nslice;
     if (per_slice < 1) return -100;
     if (per_slice > tiles) per_slice = tiles;
-    const size_t smem = tc::smem_bytes(bk, kc, ring);
-    if (bk == 32) {
-        if (cudaFuncSetAttribute(tc::fea_dense_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
-        tc::fea_dense_tc_kernel<32><<<per_slice * nslice, tc::THREADS, smem, stream>>>(mx, mb, mo, M, P, tiles, per_slice, kc, ring, relu);
-    } else {
-        if (cudaFuncSetAttribute(tc::fea_dense_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
-        tc::fea_dense_tc_kernel<16><<<per_slice * nslice, tc::THREADS, smem, stream>>>(mx, mb, mo, M, P, tiles, per_slice, kc, ring, relu);
-    }
+    const size_t smem = tc::smem_bytes(bn, bk, kc, ring);
+#define SGRACE_TC_LAUNCH(BKV, BNV)                                                                                              \
+    do {                                                                                                                        \
+        if (cudaFuncSetAttribute(tc::fea_dense_tc_kernel<BKV, BNV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=   \
+            cudaSuccess)                                                                                                        \
+            return -2;                                                                                                          \
+        tc::fea_dense_tc_kernel<BKV, BNV><<<per_slice * nslice, tc::THREADS, smem, stream>>>(mx, mb, mo, M, P, tiles, per_slice, \
+                                                                                             kc, ring, relu);                   \
+    } while (0)
+    if (bk == 32 && bn == 128) SGRACE_TC_LAUNCH(32, 128);
+    else if (bk == 16 && bn == 128) SGRACE_TC_LAUNCH(16, 128);
+    else if (bk == 32) SGRACE_TC_LAUNCH(32, 64);
+    else SGRACE_TC_LAUNCH(16, 64);
+#undef SGRACE_TC_LAUNCH
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 

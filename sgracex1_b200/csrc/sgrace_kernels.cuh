@@ -456,6 +456,62 @@ halo_push_kernel(const PushTable pt, const float4* __restrict__ local, int W4) {
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// Tall-skinny transposed product for the saved-tensor backward of the notebook layer
+// (Graph_Classification.ipynb FPYNQ.backward: grad_W = X^T (A g)):  out[M x P] = X^T . Y with
+// X [N x M], Y [N x P] row-major and N >> M, P.  Each CTA reduces a contiguous chunk of rows into a
+// 64 x 64 output tile (4 x 4 per thread, 32-row slabs through shared memory) and writes its partial
+// tile; xty_reduce_kernel adds the partial tiles in chunk order -- deterministic, no atomics.
+__global__ void __launch_bounds__(256)
+xty_partial_kernel(const float* __restrict__ X, const float* __restrict__ Y, float* __restrict__ partial, int N, int M, int P,
+                   int rows_per_cta) {
+    __shared__ __align__(16) float xs[32][64 + 4];
+    __shared__ __align__(16) float ys[32][64 + 4];
+    const int tiles_p = (P + 63) / 64;
+    const int m0 = (blockIdx.y / tiles_p) * 64, p0 = (blockIdx.y % tiles_p) * 64;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int r_begin = blockIdx.x * rows_per_cta, r_end = min(N, r_begin + rows_per_cta);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+    for (int r0 = r_begin; r0 < r_end; r0 += 32) {
+        for (int i = threadIdx.x; i < 32 * 64; i += 256) {
+            const int rr = i >> 6, cc = i & 63, r = r0 + rr;
+            xs[rr][cc] = (r < r_end && m0 + cc < M) ? __ldg(X + (size_t)r * M + m0 + cc) : 0.f;
+            ys[rr][cc] = (r < r_end && p0 + cc < P) ? __ldg(Y + (size_t)r * P + p0 + cc) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int rr = 0; rr < 32; rr++) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&xs[rr][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&ys[rr][tx * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float* dst = partial + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * 4096;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) dst[(ty * 4 + i) * 64 + tx * 4 + j] = acc[i][j];
+}
+
+__global__ void xty_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int M, int P, int chunks, int tiles) {
+    const int tiles_p = (P + 63) / 64;
+    const int t = blockIdx.x, e = threadIdx.x + blockIdx.y * blockDim.x;      // tile, element of the 64 x 64 tile
+    if (e >= 4096) return;
+    const int m = (t / tiles_p) * 64 + e / 64, pcol = (t % tiles_p) * 64 + e % 64;
+    if (m >= M || pcol >= P) return;
+    float acc = 0.f;
+    for (int c = 0; c < chunks; c++) acc += partial[((size_t)c * tiles + t) * 4096 + e];
+    out[(size_t)m * P + pcol] = acc;
+}
+
 // Generic-width fallback (P not a multiple of 4, e.g. the reference's P_w = 21 tail
 // case, K:794-799): a full warp per row, lane j owns columns j, j+32, ...
 template <int NC>

@@ -57,7 +57,11 @@ struct StreamParams {
     int static_tiles;        // tiles each CTA owns as one contiguous run before it claims dynamically
     int l1_prefetch;         // GLOBAL gathers: passes of next-row Bm prefetch per group (0 = off)
     int dry_run;             // debug: stream the stages but skip the arithmetic (feed-rate measurement)
-    int prefetch_rows;       // > 0 (GLOBAL): rows of Bm; the producer L2-prefetches Bm rows [rb, re) of a sub-tile
+    int prefetch_rows;       // > 0 (GLOBAL): rows of Bm; the producer L2-prefetches the Bm rows `prefetch_lead` rows
+                             //     ahead of each sub-tile (near-diagonal adjacencies: batched graphs, banded orderings)
+    int prefetch_lead;
+    int reverse;             // 1: tiles are walked from the last row to the first (ADJ right after FEA: the rows of XW
+                             //     written last are still in L2)
     int* long_rows;
     int* long_count;
     int* tile_counter;
@@ -238,11 +242,14 @@ spmm_stream_f32_kernel(const StreamParams p) {
                 StageHeader h;
                 h.row_begin = rb; h.nrows = re - rb; h.kbase = kb_al; h.roff = rb - rb_al;
                 hdr[stage] = h;
-                if (BSRC == BSRC_GLOBAL && p.prefetch_rows > 0 && rb < p.prefetch_rows) {
-                    // rows near the diagonal: the Bm rows this sub-tile's own rows map to
-                    const int pe = min(re, p.prefetch_rows);
-                    bulk_prefetch_l2(reinterpret_cast<const char*>(p.Bm) + (size_t)rb * p.P4 * 16,
-                                     (uint32_t)(pe - rb) * (uint32_t)p.P4 * 16u);
+                if (BSRC == BSRC_GLOBAL && p.prefetch_rows > 0) {
+                    // the band of Bm rows the walk will reach `prefetch_lead` rows from now: every row of the
+                    // band is requested once, long before the gathers that need it
+                    const int shift = p.reverse ? -p.prefetch_lead : p.prefetch_lead;
+                    const int pb = max(rb + shift, 0), pe = min(re + shift, p.prefetch_rows);
+                    if (pe > pb)
+                        bulk_prefetch_l2(reinterpret_cast<const char*>(p.Bm) + (size_t)pb * p.P4 * 16,
+                                         (uint32_t)(pe - pb) * (uint32_t)p.P4 * 16u);
                 }
             }
             __syncwarp();
@@ -264,9 +271,10 @@ spmm_stream_f32_kernel(const StreamParams p) {
             seq++;
             return t;                               // valid in lane 0 only until shuffled
         };
+        const int ntiles = (p.nrows + TR - 1) / TR;
         // piece j of a tile covers rows [a + j*SUB, a + (j+1)*SUB) clipped to the tile
         auto sample = [&](int t, int& r_lo, int& r_hi, int& s_lo, int& s_hi) {
-            const long long a_ll = (long long)t * TR;
+            const long long a_ll = t < ntiles ? (long long)(p.reverse ? ntiles - 1 - t : t) * TR : (long long)p.nrows;
             const int a = a_ll < p.nrows ? (int)a_ll : p.nrows;
             const int tile_end = min(a + TR, p.nrows);
             r_lo = min(a + lane * SUB, tile_end);
@@ -279,8 +287,8 @@ spmm_stream_f32_kernel(const StreamParams p) {
         sample(t_cur, n_rlo, n_rhi, n_slo, n_shi);
         int t_next_raw = claim();
         for (;;) {
-            if ((long long)t_cur * TR >= p.nrows) break;
-            const int a = t_cur * TR;
+            if (t_cur >= ntiles) break;
+            const int a = (p.reverse ? ntiles - 1 - t_cur : t_cur) * TR;
             const int tile_end = min(a + TR, p.nrows);
             const int r_lo = n_rlo, r_hi = n_rhi, s_lo = n_slo, s_hi = n_shi;
             // next tile: its claim was issued an iteration ago; issue its samples and the claim after it

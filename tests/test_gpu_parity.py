@@ -321,7 +321,7 @@ def test_errors_are_reported(ip):
 # ------------------------------------------------------------------------------------------
 # dense FEA on the tensor cores (tcgen05, 3xTF32): 1e-5 against the FLOAT-build oracle
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("shape", [(1000, 100, 256), (333, 64, 128), (4097, 128, 384), (129, 36, 128)])
+@pytest.mark.parametrize("shape", [(1000, 100, 256), (333, 64, 128), (4097, 128, 384), (129, 36, 128), (2050, 64, 64), (700, 100, 192)])
 def test_dense_fea_tensor_core_path(ip, shape):
     from sgracex1_b200.driver import DeviceLayer
     n, m, p = shape

@@ -1,3 +1,4 @@
-exec > gpurun_out/sanitizer_r1.log 2>&1
-compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "fast_float_widths or edge_cases or long_rows or tensor_core" 2>&1 | tail -12
-echo "exit=$?"
+exec > gpurun_out/run3.log 2>&1
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python bench.py --workload molecule --steps 20 --warmup 3 2>&1 | tail -1 | cut -c1-330
+./tools/micro/tc_fea_test 227732 64 64 | tail -2
