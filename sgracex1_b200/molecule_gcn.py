@@ -342,6 +342,34 @@ def sgrace_layer_device(handle, adj_csr, x, weight, relu):
     return out
 
 
+class _DevicePool(torch.autograd.Function):
+    """global_mean_pool as two CSR products on the accelerator's ADJ kernel: pooled = P h with
+    P[g, n] = 1/|graph g| (graphs are contiguous node ranges), grad_h = P^T grad_pooled."""
+
+    @staticmethod
+    def forward(ctx, handle, pool_csr, pool_t_csr, h, layer_fn):
+        ctx.handle, ctx.pool_t_csr, ctx.layer_fn = handle, pool_t_csr, layer_fn
+        return layer_fn(handle, pool_csr, h.contiguous(), None, False)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return None, None, None, ctx.layer_fn(ctx.handle, ctx.pool_t_csr, grad_out.contiguous(), None, False), None
+
+
+def pooling_csr(batch, num_graphs):
+    """(P, P^T) as CSR triples for a sorted `batch` vector (node -> graph)."""
+    n = batch.numel()
+    dev = batch.device
+    counts = torch.bincount(batch, minlength=num_graphs)
+    rp = torch.zeros(num_graphs + 1, dtype=torch.int32, device=dev)
+    rp[1:] = torch.cumsum(counts, 0).to(torch.int32)
+    inv = (1.0 / counts.clamp(min=1).to(torch.float32))
+    val = inv[batch].contiguous()
+    p = (rp, torch.arange(n, dtype=torch.int32, device=dev), val)
+    pt = (torch.arange(n + 1, dtype=torch.int32, device=dev), batch.to(torch.int32).contiguous(), val)
+    return p, pt
+
+
 class GCN_B200(torch.nn.Module):
     """GCN_PYNQ with device-resident buffers.  `layer_fn` is the accelerator call (default: the C
     ABI); the CPU tests of the distributed logic inject a torch stand-in."""
@@ -354,11 +382,15 @@ class GCN_B200(torch.nn.Module):
         self.conv2 = GraphConvolution_pynq(hidden_channels, hidden_channels, None)
         self.lin = Linear(hidden_channels, num_classes)
 
-    def forward(self, x, adj_csr, batch, num_graphs):
+    def forward(self, x, adj_csr, batch, num_graphs, pool=None):
+        """`pool` = pooling_csr(batch, num_graphs) computed once per batch (None: torch index_add pooling)."""
         h = _DeviceGraphLayer.apply(self.handle, adj_csr, x, self.conv1.weight, 1, self.layer_fn)
         h = RPYNQ.apply(h)
         h = _DeviceGraphLayer.apply(self.handle, adj_csr, h, self.conv2.weight, 0, self.layer_fn)
-        h = global_mean_pool(h, batch, num_graphs)
+        if pool is not None:
+            h = _DevicePool.apply(self.handle, pool[0], pool[1], h, self.layer_fn)
+        else:
+            h = global_mean_pool(h, batch, num_graphs)
         h = F.dropout(h, p=0.5, training=self.training)
         return self.lin(h)
 
@@ -421,10 +453,11 @@ def bench_molecule(args):
     y = torch.from_numpy(y_np.astype(np.int64)).to(dev)
     total_graphs = graphs_per_rank * world
     loss_buf = torch.zeros((), device=dev)
+    pool = pooling_csr(batch, graphs_per_rank)
 
     def step():
         opt.zero_grad(set_to_none=False)
-        out = model(x, adj, batch, graphs_per_rank)
+        out = model(x, adj, batch, graphs_per_rank, pool)
         loss = crit(out, y) / total_graphs
         loss.backward()
         sdist.flat_allreduce_grads(model.parameters())

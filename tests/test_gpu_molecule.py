@@ -98,7 +98,8 @@ def test_gcn_b200_device_resident_matches_stand_in():
     m_gpu = MG.GCN_B200(16, handle).to(dev).eval()
     m_cpu = MG.GCN_B200(16, None, layer_fn=torch_layer).eval()
     m_cpu.load_state_dict({k: v.cpu() for k, v in m_gpu.state_dict().items()})
-    out_g = m_gpu(d.x.to(dev), adj_dev, d.batch.to(dev), 40)
+    pool = MG.pooling_csr(d.batch.to(dev), 40)
+    out_g = m_gpu(d.x.to(dev), adj_dev, d.batch.to(dev), 40, pool)
     out_c = m_cpu(d.x, adj_cpu, d.batch, 40)
     assert torch.allclose(out_g.cpu(), out_c, rtol=1e-4, atol=1e-5)
     torch.nn.CrossEntropyLoss()(out_g, d.y.to(dev)).backward()
