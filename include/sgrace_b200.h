@@ -82,6 +82,8 @@ enum {
     SGRACE_OPT_DENSE_TC = 14,       /* 1: allow the tcgen05 path for wide dense FEA (FAST)  */
     SGRACE_OPT_STREAM_KERNEL = 15,  /* 1 (default): TMA-staged persistent SpMM kernel (FAST);
                                        0: the row-strided kernel (any pointer alignment)    */
+    SGRACE_OPT_FUSED_SMALL = 18,    /* sparse-feature FAST layers with at most this many rows run as ONE cooperative
+                                       launch (W transpose | FEA | ADJ with grid barriers); default 65536, 0 = off */
     SGRACE_OPT_ACCUMULATE = 17,     /* 1: the ADJ stage computes D = act(D + A.XW): the second pass over an
                                        adjacency split by column ownership (multi-GPU halo)  */
     SGRACE_OPT_AGG_FIRST = 16       /* 1: dense layers with M_fea < P_w run as act((A.X).W) --
@@ -212,6 +214,16 @@ int sgrace_halo_gather(sgrace_handle* h, const uint64_t* bases, int32_t n_peers,
  * the destination's first halo slot for this owner), in order */
 int sgrace_halo_push(sgrace_handle* h, const void* local, int32_t width, int32_t n_dst, const uint64_t* rows_ptrs,
                      const int64_t* counts, const uint64_t* dst_ptrs);
+
+/* the exchange without any SM: copy-engine transfers between peer-visible buffers, ordered on the
+ * handle's stream, and 32-bit flag words for the "my rows have landed" signal.
+ *   sgrace_peer_copy    dst/src are device addresses on this GPU or peer-mapped ones
+ *   sgrace_peer_signal  writes (value mod 65536) to the flag word after all earlier work on the stream
+ *   sgrace_wait_flag    makes the stream wait (stream memory operation) until the flag word, in a buffer of
+ *                       this GPU, equals (value mod 65536) */
+int sgrace_peer_copy(sgrace_handle* h, uint64_t dst, uint64_t src, size_t bytes);
+int sgrace_peer_signal(sgrace_handle* h, uint64_t flag_addr, uint32_t value);
+int sgrace_wait_flag(sgrace_handle* h, uint64_t flag_addr, uint32_t value);
 
 /* saved-tensor backward helper of the notebook layer (FPYNQ.backward: grad_W = X^T (A g)):
  * out[M x P] = X^T . Y for X [N x M], Y [N x P] row-major float32, N >> M, P; deterministic */

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libsgrace_b200.so")
 MODE_F32_FAST, MODE_F32_CSIM, MODE_F16_CSIM, MODE_FIX16_CSIM, MODE_FULL = 0, 1, 2, 3, 4
 (OPT_MODE, OPT_SPMM_BLOCK, OPT_LAT_FEA, OPT_LAT_ADJ, OPT_FEA_THREADS, OPT_ADJ_THREADS,
  OPT_USE_SBLOCKS, OPT_INDEX_FORMAT, OPT_QBITS, OPT_STAGING, OPT_LONG_ROW, OPT_LEAKY_ALPHA_BITS,
- OPT_VALIDATE, OPT_DENSE_TC, OPT_STREAM_KERNEL, OPT_AGG_FIRST, OPT_ACCUMULATE) = range(1, 18)
+ OPT_VALIDATE, OPT_DENSE_TC, OPT_STREAM_KERNEL, OPT_AGG_FIRST, OPT_ACCUMULATE, OPT_FUSED_SMALL) = range(1, 19)
 REG_CTRL, REG_MAX_FEA = 0x00, 0x70
 
 EXPORTS = (
@@ -25,6 +25,7 @@ EXPORTS = (
     "sgrace_stage_times", "sgrace_layer_run", "sgrace_fea_run", "sgrace_adj_run",
     "sgrace_launch_count", "sgrace_dense_run", "sgrace_peer_alloc", "sgrace_peer_open", "sgrace_peer_release",
     "sgrace_adj_run_peer", "sgrace_halo_gather", "sgrace_halo_push", "sgrace_xty_run",
+    "sgrace_peer_copy", "sgrace_peer_signal", "sgrace_wait_flag",
 )
 
 
@@ -95,6 +96,9 @@ def load():
     lib.sgrace_adj_run_peer.argtypes = [H, C.POINTER(LayerDesc), C.POINTER(C.c_uint64), C.c_int32, C.c_int32]
     lib.sgrace_halo_gather.argtypes = [H, C.POINTER(C.c_uint64), C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     lib.sgrace_halo_push.argtypes = [H, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_int64), C.POINTER(C.c_uint64)]
+    lib.sgrace_peer_copy.argtypes = [H, C.c_uint64, C.c_uint64, C.c_size_t]
+    lib.sgrace_peer_signal.argtypes = [H, C.c_uint64, C.c_uint32]
+    lib.sgrace_wait_flag.argtypes = [H, C.c_uint64, C.c_uint32]
     lib.sgrace_xty_run.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
     lib.sgrace_dense_run.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     for name in EXPORTS:
@@ -240,6 +244,15 @@ class Handle:
         n = len(rows_ptrs)
         self._ck(self.lib.sgrace_halo_push(self.h, C.c_void_p(local_ptr), int(width), n, (C.c_uint64 * n)(*[int(p) for p in rows_ptrs]),
                                            (C.c_int64 * n)(*[int(c) for c in counts]), (C.c_uint64 * n)(*[int(p) for p in dst_ptrs])))
+
+    def peer_copy(self, dst_addr, src_addr, nbytes):
+        self._ck(self.lib.sgrace_peer_copy(self.h, int(dst_addr), int(src_addr), int(nbytes)))
+
+    def peer_signal(self, flag_addr, value):
+        self._ck(self.lib.sgrace_peer_signal(self.h, int(flag_addr), int(value) & 0xffffffff))
+
+    def wait_flag(self, flag_addr, value):
+        self._ck(self.lib.sgrace_wait_flag(self.h, int(flag_addr), int(value) & 0xffffffff))
 
     def xty_run(self, x_ptr, y_ptr, out_ptr, N, M, P):
         self._ck(self.lib.sgrace_xty_run(self.h, C.c_void_p(x_ptr), C.c_void_p(y_ptr), C.c_void_p(out_ptr), int(N), int(M), int(P)))

@@ -49,6 +49,8 @@ struct sgrace_handle {
     int mode = SGRACE_MODE_F32_FAST;
     int spmm_block = 1, lat_fea = 0, lat_adj = 0, fea_threads = 1, adj_threads = 1, use_sblocks = 0;
     int index_format = 0, qbits = 8, staging = 1, long_row = 512, validate = 0, dense_tc = 1, stream_kernel = 1, agg_first = 0, accumulate = 0;
+    int fused_small = 65536;                    // layers with at most this many rows run as one cooperative launch (0: off)
+    unsigned counter_phase = 0;                 // which of the two counter sets the next SpMM launch uses
     // set for the duration of sgrace_adj_run_peer
     const char* peer_base[MAX_PEERS] = {nullptr};
     int peer_block = 0, peer_count = 0;
@@ -57,6 +59,7 @@ struct sgrace_handle {
     float leaky_alpha = 0.2f;
     // scratch (grow-only)
     Scratch wrm, wdup, ax, long_partial, long_done, xw, wq, s1, s2, rp_fea, rp_adj, lists, counters;
+    Scratch seq;             // seq[i] = i, the source of sgrace_peer_signal's 4-byte copies
     int smem_optin = 0;      // cudaDevAttrMaxSharedMemoryPerBlockOptin
     int* max_fea_dev = nullptr;
     // state
@@ -124,11 +127,25 @@ inline int grid_for(long long work_items, int block, int num_sms, int max_waves 
     return (int)g;
 }
 
+// Two sets of 16 int counters (long-row count, tile counter, ...) used by alternate launches: the
+// long-row kernel that ends a launch zeroes the other set, so no memset sits between the kernels.
+int counter_sets(sgrace_handle* h, int** cur, int** next) {
+    if (h->counters.bytes < 256) {
+        if (int rc = ensure(h, h->counters, 256)) return rc;
+        CU(cudaMemsetAsync(h->counters.p, 0, h->counters.bytes, h->stream));
+    }
+    int* base = (int*)h->counters.p + 16;        // ints 0..15 stay with the GAT kernels
+    *cur = base + 16 * (h->counter_phase & 1);
+    *next = base + 16 * ((h->counter_phase + 1) & 1);
+    h->counter_phase++;
+    return 0;
+}
+
 // rows the main kernel deferred (longer than the threshold / a stage): segmented CTA-per-segment kernel
 // with deterministic last-arriver combine; the row-per-CTA kernel covers lists it cannot hold
 template <int NVL>
 int launch_long_rows(sgrace_handle* h, const int* rp, const int* ci, const float* va, const float* Bm, float* out, int P4,
-                     int relu, int* long_rows, int* long_count, long long nnz_hint) {
+                     int relu, int* long_rows, int* long_count, long long nnz_hint, int* next_counters) {
     const size_t lsmem = sizeof(float4) * 8 * (size_t)P4;
     // segments <= nnz/SEG + #long rows, #long rows <= nnz/threshold
     const long long max_rows = nnz_hint > 0 ? nnz_hint / (h->long_row > 0 ? h->long_row : 1) + 1 : 0;
@@ -151,12 +168,12 @@ int launch_long_rows(sgrace_handle* h, const int* rp, const int* ci, const float
             CU(cudaFuncSetAttribute(spmm_long_rows_seg_f32_kernel<NVL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
         spmm_long_rows_seg_f32_kernel<NVL><<<h->num_sms * 4, 256, lsmem, h->stream>>>(
             rp, ci, va, (const float4*)Bm, (float4*)out, P4, relu, long_rows, long_count, (float4*)h->long_partial.p,
-            (int*)h->long_done.p, pt);
+            (int*)h->long_done.p, pt, next_counters);
     } else {
         if (lsmem > 48 * 1024)
             CU(cudaFuncSetAttribute(spmm_long_rows_f32_kernel<NVL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
         spmm_long_rows_f32_kernel<NVL><<<h->num_sms * 2, 256, lsmem, h->stream>>>(
-            rp, ci, va, (const float4*)Bm, (float4*)out, P4, relu, long_rows, long_count, pt);
+            rp, ci, va, (const float4*)Bm, (float4*)out, P4, relu, long_rows, long_count, pt, next_counters);
     }
     h->launches++;
     CU(cudaGetLastError());
@@ -174,10 +191,10 @@ int launch_spmm_vec(sgrace_handle* h, const int* rp, const int* ci, const float*
     constexpr int RPW = 32 / LPR;
     // room for the long-row list: nrows ints + counter
     if (int rc = ensure(h, h->lists, sizeof(int) * (size_t)(nrows > 0 ? nrows : 1))) return rc;
-    if (int rc = ensure(h, h->counters, 64)) return rc;
+    int *cset, *nset;
+    if (int rc = counter_sets(h, &cset, &nset)) return rc;
     int* long_rows = (int*)h->lists.p;
-    int* long_count = (int*)h->counters.p;
-    CU(cudaMemsetAsync(long_count, 0, sizeof(int), h->stream));
+    int* long_count = cset;
     const int block = 256;
     long long warps = ((long long)nrows + RPW - 1) / RPW;
     // persistent grid: exactly the CTAs that are resident at once (occupancy x SM count), each
@@ -193,7 +210,7 @@ int launch_spmm_vec(sgrace_handle* h, const int* rp, const int* ci, const float*
     h->launches++;
     CU(cudaGetLastError());
     constexpr int NVL = (LPR * NV + 31) / 32 > 0 ? (LPR * NV + 31) / 32 : 1;
-    if (int rc = launch_long_rows<NVL>(h, rp, ci, va, Bm, out, P4, relu, long_rows, long_count, 0)) return rc;
+    if (int rc = launch_long_rows<NVL>(h, rp, ci, va, Bm, out, P4, relu, long_rows, long_count, 0, nset)) return rc;
     return 0;
 }
 
@@ -207,12 +224,11 @@ int launch_spmm_stream(sgrace_handle* h, const int* rp, const int* ci, const flo
                        int nrows, int P, int relu, long long nnz_hint, int b_rows, int final_out, int b_total_rows) {
     const int P4 = P / 4;
     if (int rc = ensure(h, h->lists, sizeof(int) * (size_t)(nrows > 0 ? nrows : 1))) return rc;
-    if (int rc = ensure(h, h->counters, 64)) return rc;
+    int *cset, *nset;
+    if (int rc = counter_sets(h, &cset, &nset)) return rc;
     int* long_rows = (int*)h->lists.p;
-    int* long_count = (int*)h->counters.p;
-    int* tile_counter = (int*)h->counters.p + 2;
-    CU(cudaMemsetAsync(long_count, 0, sizeof(int), h->stream));
-    CU(cudaMemsetAsync(tile_counter, 0, sizeof(int), h->stream));
+    int* long_count = cset;
+    int* tile_counter = cset + 2;
 
     StreamParams sp;
     memset(&sp, 0, sizeof(sp));
@@ -341,7 +357,7 @@ int launch_spmm_stream(sgrace_handle* h, const int* rp, const int* ci, const flo
     CU(cudaGetLastError());
 
     constexpr int NVL = (LPR * NV + 31) / 32 > 0 ? (LPR * NV + 31) / 32 : 1;
-    if (int rc = launch_long_rows<NVL>(h, rp, ci, va, Bm, out, P4, relu, long_rows, long_count, nnz_hint)) return rc;
+    if (int rc = launch_long_rows<NVL>(h, rp, ci, va, Bm, out, P4, relu, long_rows, long_count, nnz_hint, nset)) return rc;
     return 0;
 }
 
@@ -481,6 +497,57 @@ int dense_f32(sgrace_handle* h, const float* X, const float* B, float* out, int 
     return 0;
 }
 
+// one cooperative launch per small layer; -100 = not eligible (grid does not fit / no cooperative launch)
+template <int LPR, int NV, bool SPLIT>
+int launch_fused_small_k(sgrace_handle* h, const sgrace_layer_desc* d, const int* rp_fea, const int* rp_adj, void* XW) {
+    const int N = d->N_adj, M = d->M_fea, P = d->P_w;
+    if (int rc = ensure(h, h->wrm, sizeof(float) * (size_t)M * P)) return rc;
+    { int *c0, *c1; if (int rc = counter_sets(h, &c0, &c1)) return rc; h->counter_phase--; }   // allocation only
+    auto kern = fused_small_layer_f32_kernel<LPR, NV, SPLIT>;
+    static int per_sm = -1;                     // per instantiation; one device kind per process
+    if (per_sm < 0) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+    if (per_sm < 1) return -100;
+    constexpr int RPW = SPLIT ? 1 : 32 / LPR;
+    static const int cap_per_sm = env_int("SGRACE_FUSED_CTAS_PER_SM", 4);
+    long long want = ((long long)N + RPW * 8 - 1) / (RPW * 8);        // 8 warps per CTA
+    long long cap = (long long)h->num_sms * (per_sm > cap_per_sm ? cap_per_sm : per_sm);
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    const int* ci_f = d->columnIndex_fea; const float* va_f = (const float*)d->values_fea;
+    const int* ci_a = d->columnIndex_adj; const float* va_a = (const float*)d->values_adj;
+    const float* Bp = (const float*)d->B; float* Wrm = (float*)h->wrm.p;
+    float4* XWp = (float4*)XW; float4* Dp = (float4*)d->D;
+    int Nn = N, Mm = M, Pp = P, relu = d->relu != 0;
+    static int phases = env_int("SGRACE_FUSED_PHASES", 7);
+    unsigned* bar = (unsigned*)h->counters.p + 48;      // ints 48,49: grid barrier {count, generation}
+    void* args[] = {&rp_fea, &ci_f, &va_f, &rp_adj, &ci_a, &va_a, &Bp, &Wrm, &XWp, &Dp, &Nn, &Mm, &Pp, &relu, &bar, &phases};
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(256), args, 0, h->stream);
+    if (e != cudaSuccess) { cudaGetLastError(); return -100; }
+    h->launches++;
+    return 0;
+}
+
+template <int LPR, int NV>
+int launch_fused_small_t(sgrace_handle* h, const sgrace_layer_desc* d, const int* rp_fea, const int* rp_adj, void* XW) {
+    // below this many rows a warp per row (lane groups share the row's non-zeros) shortens the critical path
+    static const int split_rows = env_int("SGRACE_FUSED_SPLIT_ROWS", 16384);
+    if (LPR < 32 && d->N_adj <= split_rows) return launch_fused_small_k<LPR, NV, true>(h, d, rp_fea, rp_adj, XW);
+    return launch_fused_small_k<LPR, NV, false>(h, d, rp_fea, rp_adj, XW);
+}
+
+int launch_fused_small(sgrace_handle* h, const sgrace_layer_desc* d, const int* rp_fea, const int* rp_adj, void* XW) {
+    const int P4 = d->P_w / 4;
+    if (P4 == 1) return launch_fused_small_t<1, 1>(h, d, rp_fea, rp_adj, XW);
+    if (P4 == 2) return launch_fused_small_t<2, 1>(h, d, rp_fea, rp_adj, XW);
+    if (P4 <= 4) return launch_fused_small_t<4, 1>(h, d, rp_fea, rp_adj, XW);
+    if (P4 <= 8) return launch_fused_small_t<8, 1>(h, d, rp_fea, rp_adj, XW);
+    if (P4 <= 16) return launch_fused_small_t<16, 1>(h, d, rp_fea, rp_adj, XW);
+    if (P4 <= 32) return launch_fused_small_t<32, 1>(h, d, rp_fea, rp_adj, XW);
+    if (P4 <= 64) return launch_fused_small_t<32, 2>(h, d, rp_fea, rp_adj, XW);
+    if (P4 <= 128) return launch_fused_small_t<32, 4>(h, d, rp_fea, rp_adj, XW);
+    return launch_fused_small_t<32, 8>(h, d, rp_fea, rp_adj, XW);
+}
+
 QConst make_qconst(const sgrace_handle* h, const sgrace_layer_desc* d) {
     QConst q;
     memset(&q, 0, sizeof(q));
@@ -609,7 +676,7 @@ int run_adj(sgrace_handle* h, const sgrace_layer_desc* d, const int* rp_adj, con
             if (int rc = ensure(h, h->s1, sizeof(float) * (size_t)xw_rows)) return rc;
             if (int rc = ensure(h, h->s2, sizeof(float) * (size_t)xw_rows)) return rc;
             if (int rc = ensure(h, h->lists, sizeof(int) * (size_t)N)) return rc;
-            if (int rc = ensure(h, h->counters, 64)) return rc;
+            { int *c0, *c1; if (int rc = counter_sets(h, &c0, &c1)) return rc; h->counter_phase--; }
             int* empty_count = (int*)h->counters.p + 1;
             CU(cudaMemsetAsync(empty_count, 0, sizeof(int), h->stream));
             gat_scores_kernel<<<(xw_rows + 255) / 256, 256, 0, h->stream>>>((const float*)XW, d->attention,
@@ -664,6 +731,18 @@ int layer_run_impl(sgrace_handle* h, const sgrace_layer_desc* d, bool timed) {
     const int *rp_fea, *rp_adj;
     if (timed) CU(cudaEventRecord(h->ev[0], h->stream));
     if (int rc = resolve_rowptrs(h, d, &rp_fea, &rp_adj, true, true)) return rc;
+    // Small sparse-feature layers: one cooperative launch for the whole layer (W transpose | FEA | ADJ)
+    if (h->mode == SGRACE_MODE_F32_FAST && d->gemm_mode == 0 && h->fused_small && d->N_adj > 0 && d->N_adj <= h->fused_small &&
+        d->P_w % 4 == 0 && d->P_w <= 1024 && d->M_fea > 0 && !h->accumulate &&
+        (((uintptr_t)XW | (uintptr_t)d->D) & 15) == 0 && d->B && d->values_fea && d->columnIndex_fea && rp_fea && rp_adj &&
+        d->columnIndex_adj && d->values_adj && d->D) {
+        const int rc = launch_fused_small(h, d, rp_fea, rp_adj, XW);
+        if (rc != -100) {
+            if (rc) return rc;
+            if (timed) { CU(cudaEventRecord(h->ev[1], h->stream)); CU(cudaEventRecord(h->ev[2], h->stream)); }
+            return 0;
+        }
+    }
     // Opt-in aggregate-first order for a dense layer that widens (M_fea < P_w):  D = act((A.X).W).
     // Equal to act(A.(X.W)) up to float rounding; gathers M_fea-wide rows instead of P_w-wide ones.
     if (h->mode == SGRACE_MODE_F32_FAST && h->agg_first && d->gemm_mode == 1 && d->M_fea < d->P_w && d->M_fea % 4 == 0 &&
@@ -835,7 +914,7 @@ int sgrace_destroy(sgrace_handle* h) {
         cudaFree(kv.second.dev);
         cudaFreeHost(kv.second.host);
     }
-    Scratch* all[] = {&h->wrm, &h->wdup, &h->ax, &h->long_partial, &h->long_done, &h->xw, &h->wq, &h->s1, &h->s2, &h->rp_fea, &h->rp_adj, &h->lists, &h->counters};
+    Scratch* all[] = {&h->wrm, &h->wdup, &h->ax, &h->long_partial, &h->long_done, &h->xw, &h->wq, &h->s1, &h->s2, &h->rp_fea, &h->rp_adj, &h->lists, &h->counters, &h->seq};
     for (Scratch* s : all) if (s->p) cudaFree(s->p);
     if (h->max_fea_dev) cudaFree(h->max_fea_dev);
     for (int i = 0; i < 5; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -949,6 +1028,7 @@ int sgrace_set_option(sgrace_handle* h, int key, int64_t v) {
         case SGRACE_OPT_STREAM_KERNEL: h->stream_kernel = v != 0; break;
         case SGRACE_OPT_AGG_FIRST: h->agg_first = v != 0; break;
         case SGRACE_OPT_ACCUMULATE: h->accumulate = v != 0; break;
+        case SGRACE_OPT_FUSED_SMALL: if (v < 0) return fail(h, SGRACE_EINVAL, "fused_small < 0"); h->fused_small = (int)v; break;
         default: return fail(h, SGRACE_EINVAL, "unknown option %d", key);
     }
     return SGRACE_OK;
@@ -974,6 +1054,7 @@ int sgrace_get_option(sgrace_handle* h, int key, int64_t* v) {
         case SGRACE_OPT_STREAM_KERNEL: *v = h->stream_kernel; break;
         case SGRACE_OPT_AGG_FIRST: *v = h->agg_first; break;
         case SGRACE_OPT_ACCUMULATE: *v = h->accumulate; break;
+        case SGRACE_OPT_FUSED_SMALL: *v = h->fused_small; break;
         default: return fail(h, SGRACE_EINVAL, "unknown option %d", key);
     }
     return SGRACE_OK;
@@ -1069,6 +1150,50 @@ int sgrace_peer_release(sgrace_handle* h) {
     h->peer_opened.clear();
     for (auto& kv : h->peer_allocs) cudaFree((void*)(uintptr_t)kv.first);
     h->peer_allocs.clear();
+    return SGRACE_OK;
+}
+
+int sgrace_peer_copy(sgrace_handle* h, uint64_t dst, uint64_t src, size_t bytes) {
+    if (!h) return SGRACE_EINVAL;
+    h->last_status = 0;
+    CU(cudaSetDevice(h->device));
+    if (bytes == 0) return SGRACE_OK;
+    if (!dst || !src) return fail(h, SGRACE_EINVAL, "peer copy: null address");
+    CU(cudaMemcpyAsync((void*)(uintptr_t)dst, (const void*)(uintptr_t)src, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    return SGRACE_OK;
+}
+
+int sgrace_peer_signal(sgrace_handle* h, uint64_t flag_addr, uint32_t value) {
+    if (!h) return SGRACE_EINVAL;
+    h->last_status = 0;
+    CU(cudaSetDevice(h->device));
+    if (!flag_addr || (flag_addr & 3)) return fail(h, SGRACE_EINVAL, "peer signal: bad flag address");
+    if (!h->seq.p) {
+        if (int rc = ensure(h, h->seq, sizeof(uint32_t) * 65536)) return rc;
+        iota_u32_kernel<<<64, 1024, 0, h->stream>>>((uint32_t*)h->seq.p, 65536);
+        CU(cudaGetLastError());
+        h->launches++;
+    }
+    CU(cudaMemcpyAsync((void*)(uintptr_t)flag_addr, (const uint32_t*)h->seq.p + (value & 0xffffu), 4, cudaMemcpyDeviceToDevice, h->stream));
+    return SGRACE_OK;
+}
+
+int sgrace_wait_flag(sgrace_handle* h, uint64_t flag_addr, uint32_t value) {
+    if (!h) return SGRACE_EINVAL;
+    h->last_status = 0;
+    CU(cudaSetDevice(h->device));
+    if (!flag_addr || (flag_addr & 3)) return fail(h, SGRACE_EINVAL, "wait flag: bad flag address");
+    typedef CUresult (*WaitValueFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+    static WaitValueFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<WaitValueFn>(p);
+    }
+    if (!fn) return fail(h, SGRACE_EUNSUPPORTED, "cuStreamWaitValue32 is not available in this driver");
+    const CUresult r = fn((CUstream)h->stream, (CUdeviceptr)flag_addr, (cuuint32_t)(value & 0xffffu), CU_STREAM_WAIT_VALUE_EQ);
+    if (r != CUDA_SUCCESS) return fail(h, SGRACE_ECUDA, "cuStreamWaitValue32 failed (%d)", (int)r);
     return SGRACE_OK;
 }
 

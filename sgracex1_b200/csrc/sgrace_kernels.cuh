@@ -95,11 +95,11 @@ __global__ void coo_rows_to_rowptr_kernel(const int* __restrict__ rows, int nnz,
 // graphs).  Accumulation is float FMA in CSR order per row: deterministic, no atomics.
 // ---------------------------------------------------------------------------------
 template <int LPR, int NV>
-__global__ void __launch_bounds__(256)
-spmm_csr_f32_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
-                    const float* __restrict__ val, const float4* __restrict__ Bm,
-                    float4* __restrict__ out, int nrows, int P4, int relu, int long_thresh,
-                    int* __restrict__ long_rows, int* __restrict__ long_count) {
+__device__ __forceinline__ void
+spmm_csr_f32_body(const int* __restrict__ rowptr, const int* __restrict__ col,
+                  const float* __restrict__ val, const float4* __restrict__ Bm,
+                  float4* __restrict__ out, int nrows, int P4, int relu, int long_thresh,
+                  int* __restrict__ long_rows, int* __restrict__ long_count) {
     constexpr int RPW = 32 / LPR;                 // rows per warp
     constexpr int STEP = LPR < 8 ? LPR : 8;       // non-zeros fetched per group request
     constexpr int BATCH = (STEP * NV <= 8) ? STEP : (NV >= 8 ? 1 : 8 / NV);   // gathers in flight per lane
@@ -188,6 +188,185 @@ spmm_csr_f32_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
     }
 }
 
+template <int LPR, int NV>
+__global__ void __launch_bounds__(256)
+spmm_csr_f32_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+                    const float* __restrict__ val, const float4* __restrict__ Bm,
+                    float4* __restrict__ out, int nrows, int P4, int relu, int long_thresh,
+                    int* __restrict__ long_rows, int* __restrict__ long_count) {
+    spmm_csr_f32_body<LPR, NV>(rowptr, col, val, Bm, out, nrows, P4, relu, long_thresh, long_rows, long_count);
+}
+
+// ---------------------------------------------------------------------------------
+// Small graphs (one Cora-size graph, one molecule batch): the whole layer in ONE cooperative launch.
+// The streaming kernel's fixed costs (W image per CTA, tile claims, three more launches) dominate
+// below ~100k rows; here every phase is the plain row-strided traversal over all resident warps with
+// a grid-wide barrier between the phases:  W^T -> W (row-major scratch) | XW = X.W | D = act(A.XW).
+// The read-only (ld.global.nc) path is not used for XW, which this same kernel has just written.
+// ---------------------------------------------------------------------------------
+// bar[0] counts arrivals, bar[1] is the generation.  The last CTA to arrive clears the count and bumps the
+// generation, so the pair returns to its resting state and needs no host-side reset between launches.
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblk) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile unsigned* gen = bar + 1;
+        const unsigned g = *gen;                 // cannot advance before this CTA has arrived
+        __threadfence();
+        if (atomicAdd(bar, 1u) == nblk - 1) {
+            bar[0] = 0;
+            __threadfence();
+            atomicAdd(bar + 1, 1u);
+        } else {
+            while (*gen == g) { }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <int LPR, int NV>
+__device__ __forceinline__ void
+spmm_rows_plain(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ val,
+                const float4* Bm, float4* __restrict__ out, int nrows, int P4, int relu) {
+    constexpr int RPW = 32 / LPR;
+    const int lane = threadIdx.x & 31, g = lane / LPR, l = lane % LPR;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long row = warp0 * RPW + g; row < nrows; row += nwarps * RPW) {
+        const int beg = rowptr[row], end = rowptr[row + 1];
+        float4 acc[NV];
+#pragma unroll
+        for (int v = 0; v < NV; v++) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        int k = beg;
+        for (; k + 4 <= end; k += 4) {            // four gathers in flight
+            int c[4]; float a[4]; float4 b[4][NV];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { c[i] = __ldg(col + k + i); a[i] = __ldg(val + k + i); }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int v = 0; v < NV; v++) {
+                    b[i][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (v * LPR + l < P4) b[i][v] = __ldcg(Bm + (size_t)c[i] * P4 + v * LPR + l);
+                }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int v = 0; v < NV; v++) fma4(acc[v], a[i], b[i][v]);
+        }
+        for (; k < end; k++) {
+            const int c = __ldg(col + k);
+            const float a = __ldg(val + k);
+#pragma unroll
+            for (int v = 0; v < NV; v++)
+                if (v * LPR + l < P4) fma4(acc[v], a, __ldcg(Bm + (size_t)c * P4 + v * LPR + l));
+        }
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+            const int q = v * LPR + l;
+            if (q < P4) {
+                float4 r = acc[v];
+                if (relu) {
+                    r.x = r.x > 0.f ? r.x : 0.f; r.y = r.y > 0.f ? r.y : 0.f;
+                    r.z = r.z > 0.f ? r.z : 0.f; r.w = r.w > 0.f ? r.w : 0.f;
+                }
+                out[(size_t)row * P4 + q] = r;
+            }
+        }
+    }
+}
+
+// One row per warp: the 32/LPR lane groups take alternate non-zeros (two gathers in flight each) and
+// are combined with shuffles in a fixed order.  A hub row of a small graph is otherwise one serial
+// chain of L2 round trips that the rest of the grid waits for at the barrier.
+template <int LPR, int NV>
+__device__ __forceinline__ void
+spmm_rows_split(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ val,
+                const float4* Bm, float4* __restrict__ out, int nrows, int P4, int relu) {
+    constexpr int G = 32 / LPR;
+    const int lane = threadIdx.x & 31, g = lane / LPR, l = lane % LPR;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long row = warp0; row < nrows; row += nwarps) {
+        const int beg = rowptr[row], end = rowptr[row + 1];
+        float4 acc[NV];
+#pragma unroll
+        for (int v = 0; v < NV; v++) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = beg + g; k < end; k += 2 * G) {
+            const int k1 = k + G;
+            const bool has1 = k1 < end;
+            const int c0 = __ldg(col + k), c1 = has1 ? __ldg(col + k1) : c0;
+            const float a0 = __ldg(val + k), a1 = has1 ? __ldg(val + k1) : 0.f;
+            float4 b0[NV], b1[NV];
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+                b0[v] = b1[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (v * LPR + l < P4) {
+                    b0[v] = __ldcg(Bm + (size_t)c0 * P4 + v * LPR + l);
+                    b1[v] = __ldcg(Bm + (size_t)c1 * P4 + v * LPR + l);
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < NV; v++) { fma4(acc[v], a0, b0[v]); fma4(acc[v], a1, b1[v]); }
+        }
+#pragma unroll
+        for (int off = LPR; off < 32; off <<= 1)
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+                acc[v].x += __shfl_xor_sync(0xffffffffu, acc[v].x, off);
+                acc[v].y += __shfl_xor_sync(0xffffffffu, acc[v].y, off);
+                acc[v].z += __shfl_xor_sync(0xffffffffu, acc[v].z, off);
+                acc[v].w += __shfl_xor_sync(0xffffffffu, acc[v].w, off);
+            }
+        if (g == 0) {
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+                const int q = v * LPR + l;
+                if (q < P4) {
+                    float4 r = acc[v];
+                    if (relu) {
+                        r.x = r.x > 0.f ? r.x : 0.f; r.y = r.y > 0.f ? r.y : 0.f;
+                        r.z = r.z > 0.f ? r.z : 0.f; r.w = r.w > 0.f ? r.w : 0.f;
+                    }
+                    out[(size_t)row * P4 + q] = r;
+                }
+            }
+        }
+    }
+}
+
+template <int LPR, int NV, bool SPLIT>
+__global__ void __launch_bounds__(256)
+fused_small_layer_f32_kernel(const int* __restrict__ rp_fea, const int* __restrict__ ci_fea, const float* __restrict__ va_fea,
+                             const int* __restrict__ rp_adj, const int* __restrict__ ci_adj, const float* __restrict__ va_adj,
+                             const float* __restrict__ B, float* __restrict__ Wrm, float4* __restrict__ XW,
+                             float4* __restrict__ D, int N, int M, int P, int relu, unsigned* __restrict__ barrier, int phases) {
+    // `barrier` is the handle's self-resetting {count, generation} pair; `phases` (7 = all) lets a timing
+    // experiment leave a phase out
+    const unsigned nblk = gridDim.x;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+    if (phases & 1)
+        for (long long i = tid; i < (long long)M * P; i += nthr) {        // W[m][p] = B[p][m]
+            const int m = (int)(i / P), pcol = (int)(i % P);
+            Wrm[i] = __ldg(B + (size_t)pcol * M + m);
+        }
+    grid_barrier(barrier, nblk);
+    if (phases & 2) {
+        if (SPLIT) spmm_rows_split<LPR, NV>(rp_fea, ci_fea, va_fea, reinterpret_cast<const float4*>(Wrm), XW, N, P / 4, 0);
+        else spmm_rows_plain<LPR, NV>(rp_fea, ci_fea, va_fea, reinterpret_cast<const float4*>(Wrm), XW, N, P / 4, 0);
+    }
+    grid_barrier(barrier, nblk);
+    if (phases & 4) {
+        if (SPLIT) spmm_rows_split<LPR, NV>(rp_adj, ci_adj, va_adj, XW, D, N, P / 4, relu);
+        else spmm_rows_plain<LPR, NV>(rp_adj, ci_adj, va_adj, XW, D, N, P / 4, relu);
+    }
+}
+
+__global__ void iota_u32_kernel(uint32_t* out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)i;
+}
+
 // Long rows: one CTA per listed row.  Each warp walks a contiguous slice of the row's
 // non-zeros; lanes own float4 column chunks (q = lane, lane+32, ...), warps' partials
 // are combined in warp order through shared memory -> deterministic.
@@ -251,8 +430,10 @@ __global__ void __launch_bounds__(256)
 spmm_long_rows_f32_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
                           const float* __restrict__ val, const float4* __restrict__ Bm,
                           float4* __restrict__ out, int P4, int relu,
-                          const int* __restrict__ long_rows, const int* __restrict__ long_count, const PeerTable pt) {
+                          const int* __restrict__ long_rows, const int* __restrict__ long_count, const PeerTable pt,
+                          int* __restrict__ next_counters) {
     extern __shared__ float4 red[];               // [nwarp][P4]
+    if (next_counters && blockIdx.x == 0 && threadIdx.x < 16) next_counters[threadIdx.x] = 0;   // the set the NEXT launch uses
     spmm_long_rows_per_row<NV>(rowptr, col, val, Bm, out, P4, relu, long_rows, long_count, red, pt);
 }
 
@@ -270,12 +451,15 @@ __global__ void __launch_bounds__(256)
 spmm_long_rows_seg_f32_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ val,
                               const float4* __restrict__ Bm, float4* __restrict__ out, int P4, int relu,
                               const int* __restrict__ long_rows, const int* __restrict__ long_count,
-                              float4* __restrict__ partial, int* __restrict__ row_done, const PeerTable pt) {
+                              float4* __restrict__ partial, int* __restrict__ row_done, const PeerTable pt,
+                              int* __restrict__ next_counters) {
     extern __shared__ float4 red[];                               // [8 warps][P4]
     __shared__ int pref[LONG_LIST_MAX + 1];
     __shared__ int tsum[256];
     __shared__ int is_last;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // counters come in two sets used by alternate launches: this launch clears the set of the next one
+    if (next_counters && blockIdx.x == 0 && threadIdx.x < 16) next_counters[threadIdx.x] = 0;
     const int count = *long_count;
     if (count == 0) return;
     if (count > LONG_LIST_MAX) {                                  // list too long for the shared prefix: row per CTA

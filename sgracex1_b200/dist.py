@@ -135,8 +135,8 @@ def abi_adj_fn(handle):
 class _RawCuda:
     """A raw device pointer dressed up for torch.as_tensor (zero copy)."""
 
-    def __init__(self, ptr, shape):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 3,
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3,
                                          "strides": None}
 
 
@@ -253,18 +253,24 @@ class HaloLayer:
         # the concurrent exchange (and its NCCL completion signal) is starved until that kernel drains
         self.overlap = bool(os.environ.get("SGRACE_HALO_OVERLAP"))
         self.halo_rows = up(halo_rows)
+        self.halo_rows_np = halo_rows
         addr, ipc = handle_main.peer_alloc((self.block + max(self.n_halo, 1)) * width * 4)
         self.addr = addr
-        if exchange == "defer":          # single-process emulation of several ranks: the caller fills .bases
-            self.bases = None
+        # one 32-bit flag per sender ("my rows of this layer have landed"), peer-visible like the halo itself
+        self.flag_addr, flag_ipc = handle_main.peer_alloc(256)
+        torch.as_tensor(_RawCuda(self.flag_addr, (64,), "<i4"), device=device).zero_()
+        self.epoch = 0
+        if exchange == "defer":          # single-process emulation of several ranks: the caller fills .bases / .flag_bases
+            self.bases = self.flag_bases = None
         else:
             if exchange is None:
                 def exchange(mine):
                     out = [None] * world
                     dist.all_gather_object(out, mine)
                     return out
-            handles = exchange(ipc) if world > 1 else [ipc]
-            self.bases = [addr if r == rank else handle_main.peer_open(handles[r]) for r in range(world)]
+            handles = exchange((ipc, flag_ipc)) if world > 1 else [(ipc, flag_ipc)]
+            self.bases = [addr if r == rank else handle_main.peer_open(handles[r][0]) for r in range(world)]
+            self.flag_bases = [self.flag_addr if r == rank else handle_main.peer_open(handles[r][1]) for r in range(world)]
         self.buf = torch.as_tensor(_RawCuda(addr, (self.block + max(self.n_halo, 1), width)), device=device)
         self.buf.zero_()
         self.local = self.buf[:self.block]          # this rank's rows of X go here
@@ -279,27 +285,33 @@ class HaloLayer:
         self.ev_ready, self.ev_halo = torch.cuda.Event(), torch.cuda.Event()
         self._token = torch.zeros(1, device=device)
 
+    def _halo_wants(self, halo_rows):
+        """{owner: (first halo slot, global row ids)}: what this rank needs from every other rank."""
+        bounds = np.searchsorted(halo_rows, [o * self.block for o in range(self.world + 1)])
+        return bounds, {o: (int(bounds[o]), halo_rows[bounds[o]:bounds[o + 1]]) for o in range(self.world) if o != self.rank}
+
     def _exchange_push_lists(self, halo_rows, device, gather=None):
         """halo_rows is sorted, so the rows wanted from owner o are one contiguous run of halo slots."""
         import torch
-        bounds = np.searchsorted(halo_rows, [o * self.block for o in range(self.world + 1)])
-        want = {o: (int(bounds[o]), halo_rows[bounds[o]:bounds[o + 1]]) for o in range(self.world) if o != self.rank}
+        bounds, want = self._halo_wants(halo_rows)
         if gather is None:
             allw = [None] * self.world
             dist.all_gather_object(allw, want)
         else:
             allw = gather(want)
-        rows_t, counts, dsts = [], [], []
+        rows_t, counts, dsts, ranks = [], [], [], []
         for r in range(self.world):
             if r == self.rank or self.rank not in allw[r]:
                 continue
             slot0, rows = allw[r][self.rank]
             if len(rows) == 0:
                 continue
+            ranks.append(r)
             rows_t.append(torch.from_numpy(np.ascontiguousarray(rows.astype(np.int64) - self.lo).astype(np.int32)).to(device))
             counts.append(len(rows))
             dsts.append(self.bases[r] + (self.block + slot0) * self.width * 4)
         self.push = (rows_t, counts, dsts)
+        self.push_ranks = ranks
         # the same exchange through NCCL all-to-all: pack locally, one all_to_all_single into the halo region
         send_counts = [0] * self.world
         k = 0
@@ -330,15 +342,41 @@ class HaloLayer:
         """X_local must be in self.local and every rank must have reached this point (the caller's
         barrier / token all-reduce on the main stream precedes this call).  `timing`: optional dict that
         receives per-phase milliseconds (synchronises; for diagnosis only)."""
+        return self.forward_end(self.forward_begin(timing), W, relu)
+
+    def forward_begin(self, timing=None):
+        """Everything that does not depend on another rank's data: the halo exchange is started and, in the
+        overlapped orders, the owned columns are aggregated.  Nothing issued here waits for a peer."""
         import torch
         n = self.hi - self.lo
         t = torch.empty(n, self.width, dtype=torch.float32, device=self.buf.device)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)] if timing is not None else None
+        mode = os.environ.get("SGRACE_HALO_EXCHANGE", "a2a")      # a2a | dma | push | pull
+        dma = self.push is not None and mode == "dma"
+        overlap = self.overlap or (dma and os.environ.get("SGRACE_HALO_OVERLAP") != "0")
+        if dma:
+            # pack on the main stream (it must not queue behind the aggregation kernel, which holds every SM);
+            # everything that follows on the halo stream is copy-engine work and stream memory operations
+            rows_t, counts, dsts = self.push
+            sb = self.a2a["send"]
+            offs = [int(o) * self.width * 4 for o in np.concatenate([[0], np.cumsum(counts)])[:-1]]
+            if ev: ev[4].record(self.s_main)
+            self.hm.halo_push(self.local.data_ptr(), self.width, [t_.data_ptr() for t_ in rows_t], counts,
+                              [sb.data_ptr() + o for o in offs])
         self.ev_ready.record(self.s_main)
-        if self.n_halo or self.push is not None:
+        if dma:
+            self.s_halo.wait_event(self.ev_ready)
+            self.epoch += 1
+            by_rank = {r: k for k, r in enumerate(self.push_ranks)}
+            for step in range(1, self.world):           # ring order: every step is a permutation, no ingress contention
+                r = (self.rank + step) % self.world
+                k = by_rank.get(r)
+                if k is not None:
+                    self.hh.peer_copy(dsts[k], sb.data_ptr() + offs[k], counts[k] * self.width * 4)
+                self.hh.peer_signal(self.flag_bases[r] + 4 * self.rank, self.epoch)
+        elif self.n_halo or self.push is not None:
             self.s_halo.wait_event(self.ev_ready)
             if ev: ev[4].record(self.s_halo)
-            mode = os.environ.get("SGRACE_HALO_EXCHANGE", "a2a")      # a2a | push | pull
             if self.push is not None and mode == "a2a":
                 # pack the rows every destination wants (our kernel), one NCCL all-to-all straight into the halo
                 # region: measured 0.69 ms for 237 MB per rank on 8 GPUs, against 0.85 ms for bulk-store pushes
@@ -361,15 +399,30 @@ class HaloLayer:
             if ev: ev[5].record(self.s_halo)
             self.ev_halo.record(self.s_halo)
         if ev: ev[0].record(self.s_main)
-        if self.overlap:
+        if overlap:
             self._adj(self.a_loc, t, False)
             if ev: ev[1].record(self.s_main)
+        return dict(t=t, ev=ev, dma=dma, overlap=overlap, timing=timing)
+
+    def forward_end(self, st, W, relu):
+        """The part that needs the peers' rows: wait for the halo, aggregate what is left, dense stage."""
+        import torch
+        t, ev, dma, overlap, timing = st["t"], st["ev"], st["dma"], st["overlap"], st["timing"]
+        n = self.hi - self.lo
+        if dma:
+            # the waits are issued after the aggregation launch above, so that even on a shared hardware queue
+            # they cannot hold it back
+            for r in range(self.world):
+                if r != self.rank:
+                    self.hh.wait_flag(self.flag_addr + 4 * r, self.epoch)
+            if ev: ev[5].record(self.s_halo)
+            self.ev_halo.record(self.s_halo)
+        if self.n_halo or self.push is not None:
+            self.s_main.wait_event(self.ev_halo)
+        if overlap:
             if self.n_halo:
-                self.s_main.wait_event(self.ev_halo)
                 self._adj(self.a_rem, t, True)
         else:
-            if self.n_halo or self.push is not None:
-                self.s_main.wait_event(self.ev_halo)
             if ev: ev[1].record(self.s_main)
             self._adj(self.a_all, t, False)
         if ev: ev[2].record(self.s_main)

@@ -219,3 +219,57 @@ def test_halo_layer_three_emulated_ranks_on_one_gpu():
         assert lay.n_halo > 0 and lay.nnz_remote > 0
         U.assert_close_f32(out.cpu().numpy(), want[lo:hi], what=f"halo layer rank {r}")
     hm.peer_release()
+
+
+def test_halo_layer_copy_engine_exchange_three_emulated_ranks(monkeypatch):
+    """The SM-free exchange (pack, copy-engine transfers, flag words, stream waits) with the owned columns
+    aggregated while the halo travels: three emulated ranks on one GPU, each with its own streams and
+    handles, two layers back to back (the flags carry an epoch)."""
+    monkeypatch.setenv("SGRACE_HALO_EXCHANGE", "dma")
+    n, m, p = 3000, 100, 256
+    pr = U.random_problem(29, n=n, m=m, p=p, avg_deg=8)
+    rp, ci, va = pr["adj"]
+    x, W = pr["x"], pr["W"]
+    adj_c = (torch.from_numpy(rp), torch.from_numpy(ci), torch.from_numpy(va))
+    dev = torch.device("cuda:0")
+    world = 3
+    layers, streams, handles = [], [], []
+    for r in range(world):
+        st = torch.cuda.Stream()
+        hm, hh = _lib.Handle(0), _lib.Handle(0)
+        for h in (hm, hh):
+            h.set_option(_lib.OPT_STAGING, 0)
+            h.set_option(_lib.OPT_MODE, _lib.MODE_F32_FAST)
+        hm.set_stream(st.cuda_stream)
+        lo, hi = sdist.row_range(n, r, world)
+        loc = sdist.csr_row_slice(rp, ci, va, lo, hi)
+        with torch.cuda.stream(st):
+            lay = sdist.HaloLayer(hm, hh, loc, n, m, r, world, dev, exchange="defer")
+        layers.append(lay); streams.append(st); handles.append((hm, hh))
+    wants = [lay._halo_wants(lay.halo_rows_np)[1] for lay in layers]
+    for lay in layers:
+        lay.bases = [l2.addr for l2 in layers]
+        lay.flag_bases = [l2.flag_addr for l2 in layers]
+        lay._exchange_push_lists(lay.halo_rows_np, dev, gather=lambda w: wants)
+    Wd = torch.from_numpy(W).to(dev)
+    torch.cuda.synchronize()
+    for rep in range(2):
+        xs = x * (rep + 1)
+        want = torch_adj(adj_c, torch.from_numpy(xs @ W), 1).numpy()
+        for r, lay in enumerate(layers):
+            lo, hi = sdist.row_range(n, r, world)
+            lay.local[:hi - lo].copy_(torch.from_numpy(xs[lo:hi]).to(dev))
+        torch.cuda.synchronize()
+        outs, states = [], []
+        for r, lay in enumerate(layers):          # every rank sends and signals ...
+            with torch.cuda.stream(streams[r]):
+                states.append(lay.forward_begin())
+        for r, lay in enumerate(layers):          # ... before any rank's stream starts waiting for its flags
+            with torch.cuda.stream(streams[r]):
+                outs.append(lay.forward_end(states[r], Wd, 1)[0])
+        torch.cuda.synchronize()
+        for r, out in enumerate(outs):
+            lo, hi = sdist.row_range(n, r, world)
+            U.assert_close_f32(out.cpu().numpy(), want[lo:hi], what=f"dma halo layer rank {r} rep {rep}")
+    for hm, _ in handles:
+        hm.peer_release()

@@ -27,7 +27,8 @@ def run_host(ip, mode, *, N, M, P, adj, B, fea=None, x_dense=None, relu=0, coo=F
     from sgracex1_b200.driver import HostLayer
     ip.configure(spmm_block=opts.get("spmm_block", 1), lat_fea=opts.get("lat_fea", 0), lat_adj=opts.get("lat_adj", 0),
                  fea_threads=opts.get("fea_threads", 1), adj_threads=opts.get("adj_threads", 1),
-                 use_sblocks=opts.get("use_sblocks", 0), staging=1, long_row=opts.get("long_row", 512))
+                 use_sblocks=opts.get("use_sblocks", 0), staging=1, long_row=opts.get("long_row", 512),
+                 fused_small=opts.get("fused_small", 65536))
     hl = HostLayer(ip, mode, N=N, M=M, P=P, nnz_adj=len(adj[1]), nnz_fea=(len(fea[1]) if fea is not None else 0),
                    dense=x_dense is not None, coo=coo)
     try:
@@ -115,13 +116,14 @@ def test_use_sblocks_drops_relu(ip):
 # ------------------------------------------------------------------------------------------
 # fast float32 path: 1e-5 relative against the FLOAT-build oracle
 # ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fused", [0, 65536])        # 0: streaming kernels; 65536: the single cooperative launch for small layers
 @pytest.mark.parametrize("P", [4, 8, 16, 20, 21, 32, 64, 100, 128, 256])
-def test_fast_float_widths(ip, P):
+def test_fast_float_widths(ip, P, fused):
     pr = U.random_problem(P, n=301, m=40, p=P)
     adj, fea, B, xd = U.to_storage_problem(pr, O.F32)
     for relu in (0, 1):
         ref = O.layer(dtype=O.F32, N=301, M_fea=40, P=P, adj=adj, fea=fea, B=B, relu=relu)
-        got = run_host(ip, _lib.MODE_F32_FAST, N=301, M=40, P=P, adj=adj, fea=fea, B=B, relu=relu)
+        got = run_host(ip, _lib.MODE_F32_FAST, N=301, M=40, P=P, adj=adj, fea=fea, B=B, relu=relu, fused_small=fused)
         if relu:   # an element within rounding of zero may flip sign; compare where the oracle is clearly positive
             assert ((got == 0) | (got > 0)).all()
         U.assert_close_f32(got, ref, what=f"sparse P={P} relu={relu}")
@@ -149,9 +151,10 @@ def test_fast_float_long_rows_and_coo(ip):
     ref = O.layer(dtype=O.F32, N=1500, M_fea=30, P=16, adj=adj, fea=fea, B=B, relu=1)
     for coo in (False, True):
         for long_row in (64, 100000):
-            got = run_host(ip, _lib.MODE_F32_FAST, N=1500, M=30, P=16, adj=adj, fea=fea, B=B, relu=1, coo=coo,
-                           long_row=long_row)
-            U.assert_close_f32(got, ref, what=f"long rows coo={coo} long_row={long_row}")
+            for fused in (0, 65536):
+                got = run_host(ip, _lib.MODE_F32_FAST, N=1500, M=30, P=16, adj=adj, fea=fea, B=B, relu=1, coo=coo,
+                               long_row=long_row, fused_small=fused)
+                U.assert_close_f32(got, ref, what=f"long rows coo={coo} long_row={long_row} fused={fused}")
 
 
 def test_edge_cases(ip):
@@ -163,19 +166,21 @@ def test_edge_cases(ip):
     pr = U.random_problem(1, n=5, m=3, p=4)
     _, fea, B, _ = U.to_storage_problem(pr, O.F32)
     for mode in (_lib.MODE_F32_FAST, _lib.MODE_F32_CSIM):
-        D = run_host(ip, mode, N=5, M=3, P=4, adj=empty, fea=fea, B=B)
-        assert np.array_equal(D, np.zeros((5, 4), np.float32))
-        D = run_host(ip, mode, N=5, M=3, P=4, adj=pr["adj"], fea=empty, B=B)
-        assert np.array_equal(D, np.zeros((5, 4), np.float32))
+        for fused in (0, 65536):
+            D = run_host(ip, mode, N=5, M=3, P=4, adj=empty, fea=fea, B=B, fused_small=fused)
+            assert np.array_equal(D, np.zeros((5, 4), np.float32))
+            D = run_host(ip, mode, N=5, M=3, P=4, adj=pr["adj"], fea=empty, B=B, fused_small=fused)
+            assert np.array_equal(D, np.zeros((5, 4), np.float32))
 
 
 def test_cora_shape_and_block_diagonal_batch(ip):
     p = G.cora_shape(seed=0)
     ref = O.layer(dtype=O.F32, N=p.N, M_fea=p.M, P=p.P, adj=(p.adj_rowptr, p.adj_col, p.adj_val),
                   fea=(p.fea_rowptr, p.fea_col, p.fea_val), B=p.B, relu=1)
-    got = run_host(ip, _lib.MODE_F32_FAST, N=p.N, M=p.M, P=p.P, adj=(p.adj_rowptr, p.adj_col, p.adj_val),
-                   fea=(p.fea_rowptr, p.fea_col, p.fea_val), B=p.B, relu=1)
-    U.assert_close_f32(got, ref, what="cora shape")
+    for fused in (0, 65536):
+        got = run_host(ip, _lib.MODE_F32_FAST, N=p.N, M=p.M, P=p.P, adj=(p.adj_rowptr, p.adj_col, p.adj_val),
+                       fea=(p.fea_rowptr, p.fea_col, p.fea_val), B=p.B, relu=1, fused_small=fused)
+        U.assert_close_f32(got, ref, what=f"cora shape fused={fused}")
     # block-diagonal batch: every replica must equal the single-graph result (linearity of the path)
     b = G.block_diagonal([p], 8)
     got = run_host(ip, _lib.MODE_F32_FAST, N=b.N, M=b.M, P=b.P, adj=(b.adj_rowptr, b.adj_col, b.adj_val),
