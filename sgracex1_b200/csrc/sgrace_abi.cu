@@ -127,6 +127,14 @@ inline int grid_for(long long work_items, int block, int num_sms, int max_waves 
     return (int)g;
 }
 
+// lanes per row (LPR) x float4 chunks per lane (NV) for a row of P4 16-byte chunks
+#define SGRACE_P4_DISPATCH(P4, CALL)                                                                         \
+    do {                                                                                                     \
+        if ((P4) == 1) { CALL(1, 1); } else if ((P4) == 2) { CALL(2, 1); } else if ((P4) <= 4) { CALL(4, 1); } \
+        else if ((P4) <= 8) { CALL(8, 1); } else if ((P4) <= 16) { CALL(16, 1); } else if ((P4) <= 32) { CALL(32, 1); } \
+        else if ((P4) <= 64) { CALL(32, 2); } else if ((P4) <= 128) { CALL(32, 4); } else { CALL(32, 8); }    \
+    } while (0)
+
 // Two sets of 16 int counters (long-row count, tile counter, ...) used by alternate launches: the
 // long-row kernel that ends a launch zeroes the other set, so no memset sits between the kernels.
 int counter_sets(sgrace_handle* h, int** cur, int** next) {
@@ -206,7 +214,7 @@ int launch_spmm_vec(sgrace_handle* h, const int* rp, const int* ci, const float*
     }
     int grid = grid_for(warps * 32, block, h->num_sms, ctas_per_sm);
     spmm_csr_f32_kernel<LPR, NV><<<grid, block, 0, h->stream>>>(
-        rp, ci, va, (const float4*)Bm, (float4*)out, nrows, P4, relu, h->long_row, long_rows, long_count);
+        rp, ci, va, (const float4*)Bm, (float4*)out, nrows, P4, relu, h->long_row, long_rows, long_count, h->accumulate);
     h->launches++;
     CU(cudaGetLastError());
     constexpr int NVL = (LPR * NV + 31) / 32 > 0 ? (LPR * NV + 31) / 32 : 1;
@@ -393,8 +401,8 @@ int spmm_f32(sgrace_handle* h, const int* rp, const int* ci, const float* va, co
 #undef SGRACE_STREAM
         return fail(h, SGRACE_EUNSUPPORTED, "P_w=%d > 1024 not supported", P);
     }
-    if (h->peer_count > 0 || h->accumulate)
-        return fail(h, SGRACE_EUNSUPPORTED, "peer gathers / accumulate need 16-byte aligned CSR arrays and P_w a multiple of 4");
+    if ((h->peer_count > 0 || h->accumulate) && !aligned)
+        return fail(h, SGRACE_EUNSUPPORTED, "peer gathers / accumulate need 16-byte aligned operands and P_w a multiple of 4");
     if (aligned) {
         const int P4 = P / 4;
         if (P4 == 1) return launch_spmm_vec<1, 1>(h, rp, ci, va, Bm, out, nrows, P, relu);
@@ -663,11 +671,20 @@ int run_adj(sgrace_handle* h, const sgrace_layer_desc* d, const int* rp_adj, con
         case SGRACE_MODE_FULL: {
             const QConst qc = make_qconst(h, d);
             const int quant = h->qbits > 0;
+            const bool vec = P % 4 == 0 && P <= 1024 && ((((uintptr_t)XW) | ((uintptr_t)d->D)) & 15) == 0;
             if (!d->gat_mode) {
-                long long items = (long long)N * P;
-                adj_q_gcn_kernel<<<(int)((items + 255) / 256), 256, 0, h->stream>>>(
-                    rp_adj, d->columnIndex_adj, (const float*)d->values_adj, (const float*)XW, (float*)d->D, N, P,
-                    relu, quant, qc);
+                if (vec) {
+                    const int P4 = P / 4;
+#define SGRACE_ADJQ(L, V) adj_q_gcn_vec_kernel<L, V><<<grid_for((long long)N * L, 256, h->num_sms, 64), 256, 0, h->stream>>>( \
+                        rp_adj, d->columnIndex_adj, (const float*)d->values_adj, (const float4*)XW, (float4*)d->D, N, P4, relu, quant, qc)
+                    SGRACE_P4_DISPATCH(P4, SGRACE_ADJQ);
+#undef SGRACE_ADJQ
+                } else {
+                    long long items = (long long)N * P;
+                    adj_q_gcn_kernel<<<(int)((items + 255) / 256), 256, 0, h->stream>>>(
+                        rp_adj, d->columnIndex_adj, (const float*)d->values_adj, (const float*)XW, (float*)d->D, N, P,
+                        relu, quant, qc);
+                }
                 h->launches++;
                 CU(cudaGetLastError());
                 return 0;
@@ -679,16 +696,29 @@ int run_adj(sgrace_handle* h, const sgrace_layer_desc* d, const int* rp_adj, con
             { int *c0, *c1; if (int rc = counter_sets(h, &c0, &c1)) return rc; h->counter_phase--; }
             int* empty_count = (int*)h->counters.p + 1;
             CU(cudaMemsetAsync(empty_count, 0, sizeof(int), h->stream));
-            gat_scores_kernel<<<(xw_rows + 255) / 256, 256, 0, h->stream>>>((const float*)XW, d->attention,
-                                                                            (float*)h->s1.p, (float*)h->s2.p, xw_rows,
-                                                                            P, quant, qc);
-            h->launches++;
-            CU(cudaGetLastError());
-            int grid = grid_for((long long)N * 32, 256, h->num_sms, 8);
-            gat_aggregate_kernel<<<grid, 256, 0, h->stream>>>(rp_adj, d->columnIndex_adj, (const float*)d->values_adj,
-                                                              (const float*)XW, (const float*)h->s1.p,
-                                                              (const float*)h->s2.p, (float*)d->D, d->E, d->S, N, P,
-                                                              relu, quant, qc, (int*)h->lists.p, empty_count);
+            if (vec) {
+                const int P4 = P / 4;
+                gat_scores_vec_kernel<<<(xw_rows + 255) / 256, 256, sizeof(float) * 2 * P, h->stream>>>(
+                    (const float4*)XW, d->attention, (float*)h->s1.p, (float*)h->s2.p, xw_rows, P4, quant, qc);
+                h->launches++;
+                CU(cudaGetLastError());
+#define SGRACE_GATQ(L, V) gat_aggregate_vec_kernel<L, V><<<(unsigned)(((long long)N * L + 255) / 256), 256, 0, h->stream>>>( \
+                    rp_adj, d->columnIndex_adj, (const float*)d->values_adj, (const float4*)XW, (const float*)h->s1.p,       \
+                    (const float*)h->s2.p, (float4*)d->D, d->E, d->S, N, P4, relu, quant, qc, (int*)h->lists.p, empty_count)
+                SGRACE_P4_DISPATCH(P4, SGRACE_GATQ);
+#undef SGRACE_GATQ
+            } else {
+                gat_scores_kernel<<<(xw_rows + 255) / 256, 256, 0, h->stream>>>((const float*)XW, d->attention,
+                                                                                (float*)h->s1.p, (float*)h->s2.p, xw_rows,
+                                                                                P, quant, qc);
+                h->launches++;
+                CU(cudaGetLastError());
+                int grid = grid_for((long long)N * 32, 256, h->num_sms, 8);
+                gat_aggregate_kernel<<<grid, 256, 0, h->stream>>>(rp_adj, d->columnIndex_adj, (const float*)d->values_adj,
+                                                                  (const float*)XW, (const float*)h->s1.p,
+                                                                  (const float*)h->s2.p, (float*)d->D, d->E, d->S, N, P,
+                                                                  relu, quant, qc, (int*)h->lists.p, empty_count);
+            }
             h->launches++;
             CU(cudaGetLastError());
             gat_empty_rows_kernel<<<(P + 127) / 128, 128, 0, h->stream>>>((const float*)XW, (float*)d->D, xw_rows, P,

@@ -251,7 +251,7 @@ class HaloLayer:
         # overlap = aggregate the owned columns while the halo travels, then add the remote part; the default
         # runs the exchange first and one aggregation pass after it: with a persistent kernel holding every SM
         # the concurrent exchange (and its NCCL completion signal) is starved until that kernel drains
-        self.overlap = bool(os.environ.get("SGRACE_HALO_OVERLAP"))
+        self.overlap = os.environ.get("SGRACE_HALO_OVERLAP") not in (None, "", "0")
         self.halo_rows = up(halo_rows)
         self.halo_rows_np = halo_rows
         addr, ipc = handle_main.peer_alloc((self.block + max(self.n_halo, 1)) * width * 4)
@@ -283,6 +283,15 @@ class HaloLayer:
         self.s_halo = torch.cuda.Stream(device)
         self.hh.set_stream(self.s_halo.cuda_stream)
         self.ev_ready, self.ev_halo = torch.cuda.Event(), torch.cuda.Event()
+        # more copy streams for the "dma" exchange: one copy engine does not fill the links (SGRACE_HALO_DMA_STREAMS)
+        self.copy_lanes = [(self.hh, self.s_halo, None)]
+        if exchange != "defer" and world > 1:
+            from . import _lib
+            for _ in range(3):
+                hx, sx = _lib.Handle(device.index or 0), torch.cuda.Stream(device)
+                hx.set_option(_lib.OPT_STAGING, 0)
+                hx.set_stream(sx.cuda_stream)
+                self.copy_lanes.append((hx, sx, torch.cuda.Event()))
         self._token = torch.zeros(1, device=device)
 
     def _halo_wants(self, halo_rows):
@@ -332,11 +341,18 @@ class HaloLayer:
         d.rowPtr_adj, d.columnIndex_adj, d.values_adj = rp.data_ptr(), ci.data_ptr(), va.data_ptr()
         d.nnz_adj = int(ci.numel())
         d.D = out.data_ptr()
+        # the remote part has a couple of non-zeros per row: the row-per-warp kernel keeps more rows in flight
+        # than the streaming one, whose tiles are sized for long runs of non-zeros
+        plain = accumulate and os.environ.get("SGRACE_HALO_REMOTE_KERNEL", "rows") == "rows"
         self.hm.set_option(_lib.OPT_ACCUMULATE, 1 if accumulate else 0)
+        if plain:
+            self.hm.set_option(_lib.OPT_STREAM_KERNEL, 0)
         try:
             self.hm.adj_run(d, self.buf.data_ptr(), self.buf.shape[0])
         finally:
             self.hm.set_option(_lib.OPT_ACCUMULATE, 0)
+            if plain:
+                self.hm.set_option(_lib.OPT_STREAM_KERNEL, 1)
 
     def forward(self, W, relu, timing=None):
         """X_local must be in self.local and every rank must have reached this point (the caller's
@@ -351,7 +367,7 @@ class HaloLayer:
         n = self.hi - self.lo
         t = torch.empty(n, self.width, dtype=torch.float32, device=self.buf.device)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)] if timing is not None else None
-        mode = os.environ.get("SGRACE_HALO_EXCHANGE", "a2a")      # a2a | dma | push | pull
+        mode = os.environ.get("SGRACE_HALO_EXCHANGE", "dma")      # dma | a2a | push | pull
         dma = self.push is not None and mode == "dma"
         overlap = self.overlap or (dma and os.environ.get("SGRACE_HALO_OVERLAP") != "0")
         if dma:
@@ -365,15 +381,21 @@ class HaloLayer:
                               [sb.data_ptr() + o for o in offs])
         self.ev_ready.record(self.s_main)
         if dma:
-            self.s_halo.wait_event(self.ev_ready)
+            lanes = self.copy_lanes[:max(1, min(len(self.copy_lanes), int(os.environ.get("SGRACE_HALO_DMA_STREAMS", "1"))))]
+            for _, sx, _e in lanes:
+                sx.wait_event(self.ev_ready)
             self.epoch += 1
             by_rank = {r: k for k, r in enumerate(self.push_ranks)}
             for step in range(1, self.world):           # ring order: every step is a permutation, no ingress contention
                 r = (self.rank + step) % self.world
                 k = by_rank.get(r)
+                hx = lanes[(step - 1) % len(lanes)][0]
                 if k is not None:
-                    self.hh.peer_copy(dsts[k], sb.data_ptr() + offs[k], counts[k] * self.width * 4)
-                self.hh.peer_signal(self.flag_bases[r] + 4 * self.rank, self.epoch)
+                    hx.peer_copy(dsts[k], sb.data_ptr() + offs[k], counts[k] * self.width * 4)
+                hx.peer_signal(self.flag_bases[r] + 4 * self.rank, self.epoch)
+            for _, sx, e in lanes[1:]:                   # the send buffer is free again once every lane has drained
+                e.record(sx)
+                self.s_halo.wait_event(e)
         elif self.n_halo or self.push is not None:
             self.s_halo.wait_event(self.ev_ready)
             if ev: ev[4].record(self.s_halo)
@@ -535,6 +557,31 @@ def bench_products(args):
         layer.forward(W, 1, timing=tm)
         print(f"[rank {rank}] halo layer phases: " + json.dumps({k: (round(v, 3) if isinstance(v, float) else v) for k, v in tm.items()}),
               flush=True)
+        barrier()
+    if order == "agg_first" and world > 1 and os.environ.get("SGRACE_HALO_SWEEP"):
+        # diagnosis: "mode:copy_streams:overlap,..." variants timed in this process (the graph set-up dominates a run)
+        for var in os.environ["SGRACE_HALO_SWEEP"].split(","):
+            vm, vs, vo, vk = var.split(":")
+            os.environ.update(SGRACE_HALO_EXCHANGE=vm, SGRACE_HALO_DMA_STREAMS=vs, SGRACE_HALO_OVERLAP=vo, SGRACE_HALO_REMOTE_KERNEL=vk)
+            layer.overlap = vo == "1"
+            for _ in range(3):
+                step()
+            barrier()
+            tm = {}
+            dist.all_reduce(token)
+            layer.forward(W, 1, timing=tm)
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(args.steps):
+                step()
+            s1.record()
+            barrier()
+            tv = torch.tensor([s0.elapsed_time(s1) / args.steps], dtype=torch.float64, device=dev)
+            dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                print(f"[sweep {var}] ms_per_step {tv.item():.4f} phases " +
+                      json.dumps({k: round(v, 3) for k, v in tm.items() if isinstance(v, float)}), flush=True)
         barrier()
     l0 = handle.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
