@@ -341,9 +341,9 @@ class HaloLayer:
         d.rowPtr_adj, d.columnIndex_adj, d.values_adj = rp.data_ptr(), ci.data_ptr(), va.data_ptr()
         d.nnz_adj = int(ci.numel())
         d.D = out.data_ptr()
-        # the remote part has a couple of non-zeros per row: the row-per-warp kernel keeps more rows in flight
-        # than the streaming one, whose tiles are sized for long runs of non-zeros
-        plain = accumulate and os.environ.get("SGRACE_HALO_REMOTE_KERNEL", "rows") == "rows"
+        # the remote part has a couple of non-zeros per row; the row-strided kernel (SGRACE_HALO_REMOTE_KERNEL=rows)
+        # was measured level with the streaming one on 8 GPUs (1.24 vs 1.19 ms per layer), so streaming stays
+        plain = accumulate and os.environ.get("SGRACE_HALO_REMOTE_KERNEL", "stream") == "rows"
         self.hm.set_option(_lib.OPT_ACCUMULATE, 1 if accumulate else 0)
         if plain:
             self.hm.set_option(_lib.OPT_STREAM_KERNEL, 0)
