@@ -229,6 +229,24 @@ int sgrace_wait_flag(sgrace_handle* h, uint64_t flag_addr, uint32_t value);
  * out[M x P] = X^T . Y for X [N x M], Y [N x P] row-major float32, N >> M, P; deterministic */
 int sgrace_xty_run(sgrace_handle* h, const void* X, const void* Y, void* out, int32_t N, int32_t M, int32_t P);
 
+/* ---- graph preparation on the GPU (what the reference does on the host before every forward) ----
+ * sgrace_sym_norm: sym_norm2 of demo/sgrace_lib/sgrace.py:18-51. row/col (int32, device, nnz entries) and
+ * weight (float, device, or NULL = all ones) describe the edges; nodes without a self-loop get one of weight
+ * `fill`, an existing self-loop keeps its weight; the result is sorted by (row, col):
+ *   out_val[k] = deg^-1/2[row] * w * deg^-1/2[col],  deg = row sums of w in sorted order.
+ * out_row / out_col / out_val (device) must hold `capacity` >= nnz + n_nodes entries; out_rowptr (device,
+ * n_nodes + 1 ints, may be NULL) receives the CSR row pointer of the result; *out_nnz (host) its length.
+ * Bit-equal to the torch code.  Synchronises the handle's stream (the length is returned to the host). */
+int sgrace_sym_norm(sgrace_handle* h, const int32_t* row, const int32_t* col, const float* weight, int64_t nnz,
+                    int32_t n_nodes, float fill, int64_t capacity, int32_t* out_row, int32_t* out_col, float* out_val,
+                    int32_t* out_rowptr, int64_t* out_nnz);
+/* sgrace_dense_to_csr: `to_sparse` of the feature matrix (sgrace.py:1218-1227, Graph_Classification.ipynb cell
+ * 18:53-58): X [n x m] row-major float32 (device) -> rowptr (n + 1), col / val (capacity entries), entries
+ * with X != 0 in row-major order. *out_nnz is always set; SGRACE_EBOUNDS if it exceeds `capacity` (col / val are
+ * then not written). Synchronises the handle's stream. */
+int sgrace_dense_to_csr(sgrace_handle* h, const float* X, int32_t n, int32_t m, int64_t capacity, int32_t* rowptr,
+                        int32_t* col, float* val, int64_t* out_nnz);
+
 /* number of this library's kernels launched on the handle since creation (bench evidence) */
 int sgrace_launch_count(sgrace_handle* h, uint64_t* count);
 

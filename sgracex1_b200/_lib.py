@@ -25,7 +25,7 @@ EXPORTS = (
     "sgrace_stage_times", "sgrace_layer_run", "sgrace_fea_run", "sgrace_adj_run",
     "sgrace_launch_count", "sgrace_dense_run", "sgrace_peer_alloc", "sgrace_peer_open", "sgrace_peer_release",
     "sgrace_adj_run_peer", "sgrace_halo_gather", "sgrace_halo_push", "sgrace_xty_run",
-    "sgrace_peer_copy", "sgrace_peer_signal", "sgrace_wait_flag",
+    "sgrace_peer_copy", "sgrace_peer_signal", "sgrace_wait_flag", "sgrace_sym_norm", "sgrace_dense_to_csr",
 )
 
 
@@ -99,6 +99,10 @@ def load():
     lib.sgrace_peer_copy.argtypes = [H, C.c_uint64, C.c_uint64, C.c_size_t]
     lib.sgrace_peer_signal.argtypes = [H, C.c_uint64, C.c_uint32]
     lib.sgrace_wait_flag.argtypes = [H, C.c_uint64, C.c_uint32]
+    lib.sgrace_sym_norm.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_int64, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
+    lib.sgrace_dense_to_csr.argtypes = [H, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.POINTER(C.c_int64)]
     lib.sgrace_xty_run.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
     lib.sgrace_dense_run.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     for name in EXPORTS:
@@ -253,6 +257,23 @@ class Handle:
 
     def wait_flag(self, flag_addr, value):
         self._ck(self.lib.sgrace_wait_flag(self.h, int(flag_addr), int(value) & 0xffffffff))
+
+    def sym_norm(self, row_ptr, col_ptr, weight_ptr, nnz, n_nodes, fill, capacity, out_row, out_col, out_val, out_rowptr=None):
+        """sgrace_sym_norm on device pointers; returns the length of the result."""
+        n = C.c_int64()
+        self._ck(self.lib.sgrace_sym_norm(self.h, C.c_void_p(row_ptr), C.c_void_p(col_ptr), C.c_void_p(weight_ptr or None), int(nnz),
+                                          int(n_nodes), float(fill), int(capacity), C.c_void_p(out_row), C.c_void_p(out_col),
+                                          C.c_void_p(out_val), C.c_void_p(out_rowptr or None), C.byref(n)))
+        return int(n.value)
+
+    def dense_to_csr(self, x_ptr, n, m, capacity, rowptr, col, val):
+        """sgrace_dense_to_csr; returns (status, nnz): status is SGRACE_EBOUNDS when nnz exceeds the capacity."""
+        k = C.c_int64()
+        rc = self.lib.sgrace_dense_to_csr(self.h, C.c_void_p(x_ptr), int(n), int(m), int(capacity), C.c_void_p(rowptr),
+                                          C.c_void_p(col or None), C.c_void_p(val or None), C.byref(k))
+        if rc not in (0, -5):
+            self._ck(rc)
+        return rc, int(k.value)
 
     def xty_run(self, x_ptr, y_ptr, out_ptr, N, M, P):
         self._ck(self.lib.sgrace_xty_run(self.h, C.c_void_p(x_ptr), C.c_void_p(y_ptr), C.c_void_p(out_ptr), int(N), int(M), int(P)))

@@ -9,6 +9,7 @@
 #include "sgrace_kernels.cuh"
 #include "sgrace_gemm_tc.cuh"
 #include "sgrace_spmm_stream.cuh"
+#include "sgrace_prep.cuh"
 
 #include <cuda_runtime.h>
 #include <math.h>
@@ -60,6 +61,7 @@ struct sgrace_handle {
     // scratch (grow-only)
     Scratch wrm, wdup, ax, long_partial, long_done, xw, wq, s1, s2, rp_fea, rp_adj, lists, counters;
     Scratch seq;             // seq[i] = i, the source of sgrace_peer_signal's 4-byte copies
+    Scratch prep_keys, prep_ids, prep_misc, prep_tmp;   // graph preparation (sgrace_sym_norm / sgrace_dense_to_csr)
     int smem_optin = 0;      // cudaDevAttrMaxSharedMemoryPerBlockOptin
     int* max_fea_dev = nullptr;
     // state
@@ -944,7 +946,7 @@ int sgrace_destroy(sgrace_handle* h) {
         cudaFree(kv.second.dev);
         cudaFreeHost(kv.second.host);
     }
-    Scratch* all[] = {&h->wrm, &h->wdup, &h->ax, &h->long_partial, &h->long_done, &h->xw, &h->wq, &h->s1, &h->s2, &h->rp_fea, &h->rp_adj, &h->lists, &h->counters, &h->seq};
+    Scratch* all[] = {&h->wrm, &h->wdup, &h->ax, &h->long_partial, &h->long_done, &h->xw, &h->wq, &h->s1, &h->s2, &h->rp_fea, &h->rp_adj, &h->lists, &h->counters, &h->seq, &h->prep_keys, &h->prep_ids, &h->prep_misc, &h->prep_tmp};
     for (Scratch* s : all) if (s->p) cudaFree(s->p);
     if (h->max_fea_dev) cudaFree(h->max_fea_dev);
     for (int i = 0; i < 5; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -1483,6 +1485,89 @@ int sgrace_stage_times(sgrace_handle* h, float* fea_ms, float* adj_ms, float* to
     if (fea_ms) *fea_ms = a;
     if (adj_ms) *adj_ms = b;
     if (total_ms) *total_ms = c;
+    return SGRACE_OK;
+}
+
+int sgrace_sym_norm(sgrace_handle* h, const int32_t* row, const int32_t* col, const float* weight, int64_t nnz,
+                    int32_t n_nodes, float fill, int64_t capacity, int32_t* out_row, int32_t* out_col, float* out_val,
+                    int32_t* out_rowptr, int64_t* out_nnz) {
+    if (!h) return SGRACE_EINVAL;
+    h->last_status = 0;
+    CU(cudaSetDevice(h->device));
+    if (nnz < 0 || n_nodes < 0 || (nnz && (!row || !col)) || !out_row || !out_col || !out_val || !out_nnz)
+        return fail(h, SGRACE_EINVAL, "sym_norm: bad argument");
+    const long long total = (long long)nnz + n_nodes;
+    if (total >= (1ll << 31)) return fail(h, SGRACE_EUNSUPPORTED, "sym_norm: more than 2^31 entries");
+    *out_nnz = 0;
+    if (total == 0) return SGRACE_OK;
+    const int n = n_nodes;
+    using namespace prep;
+    // scratch: keys in|out, ids in|out, misc = loop_edge[n] | counters[2] | dis[n] | rowptr[n+1] | w[total]
+    if (int rc = ensure(h, h->prep_keys, 16 * (size_t)total)) return rc;
+    if (int rc = ensure(h, h->prep_ids, 8 * (size_t)total)) return rc;
+    const size_t misc_ints = (size_t)n + 2 + n + (n + 1) + total;
+    if (int rc = ensure(h, h->prep_misc, 4 * misc_ints)) return rc;
+    unsigned long long* k0 = (unsigned long long*)h->prep_keys.p; unsigned long long* k1 = k0 + total;
+    int* i0 = (int*)h->prep_ids.p; int* i1 = i0 + total;
+    int* loop_edge = (int*)h->prep_misc.p; int* counters = loop_edge + n;
+    float* dis = (float*)(counters + 2); int* rowptr = (int*)(dis + n); float* w_sorted = (float*)(rowptr + n + 1);
+    size_t tmp_bytes = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k0, k1, i0, i1, (int)total, 0, 64, h->stream));
+    if (int rc = ensure(h, h->prep_tmp, tmp_bytes)) return rc;
+    CU(cudaMemsetAsync(loop_edge, 0xff, sizeof(int) * (size_t)n, h->stream));
+    CU(cudaMemsetAsync(counters, 0, 2 * sizeof(int), h->stream));
+    const int blocks = (int)((total + 255) / 256);
+    sym_keys_kernel<<<blocks, 256, 0, h->stream>>>(row, col, nnz, n, k0, i0, loop_edge, counters);
+    CU(cudaGetLastError());
+    tmp_bytes = h->prep_tmp.bytes;
+    CU(cub::DeviceRadixSort::SortPairs(h->prep_tmp.p, tmp_bytes, k0, k1, i0, i1, (int)total, 0, 64, h->stream));
+    int host_counters[2] = {0, 0};
+    CU(cudaMemcpyAsync(host_counters, counters, sizeof(host_counters), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (host_counters[1]) return fail(h, SGRACE_EBOUNDS, "sym_norm: %d edges with a node index outside [0, %d)", host_counters[1], n);
+    const long long kept = total - host_counters[0];
+    *out_nnz = kept;
+    if (kept > capacity) return fail(h, SGRACE_EBOUNDS, "sym_norm: result has %lld entries, capacity %lld", kept, (long long)capacity);
+    const int oblocks = (int)((kept + 255) / 256);
+    sym_emit_kernel<<<oblocks, 256, 0, h->stream>>>(k1, i1, weight, loop_edge, fill, nnz, kept, out_row, out_col, w_sorted);
+    int* rp = out_rowptr ? out_rowptr : rowptr;
+    coo_rows_to_rowptr_kernel<<<(n + 1 + 255) / 256, 256, 0, h->stream>>>(out_row, (int)kept, n, rp);
+    sym_deg_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(rp, w_sorted, n, dis);
+    sym_norm_kernel<<<oblocks, 256, 0, h->stream>>>(out_row, out_col, w_sorted, dis, kept, out_val);
+    CU(cudaGetLastError());
+    h->launches += 5;
+    return SGRACE_OK;
+}
+
+int sgrace_dense_to_csr(sgrace_handle* h, const float* X, int32_t n, int32_t m, int64_t capacity, int32_t* rowptr,
+                        int32_t* col, float* val, int64_t* out_nnz) {
+    if (!h) return SGRACE_EINVAL;
+    h->last_status = 0;
+    CU(cudaSetDevice(h->device));
+    if (n < 0 || m < 0 || !rowptr || !out_nnz || (n > 0 && m > 0 && !X)) return fail(h, SGRACE_EINVAL, "dense_to_csr: bad argument");
+    using namespace prep;
+    *out_nnz = 0;
+    CU(cudaMemsetAsync(rowptr, 0, sizeof(int) * ((size_t)n + 1), h->stream));
+    if (n == 0) { CU(cudaStreamSynchronize(h->stream)); return SGRACE_OK; }
+    const int blocks = (int)(((long long)n * 32 + 255) / 256);
+    dense_count_kernel<<<blocks, 256, 0, h->stream>>>(X, n, m, rowptr);
+    CU(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, rowptr, rowptr, n + 1, h->stream));
+    if (int rc = ensure(h, h->prep_tmp, tmp_bytes)) return rc;
+    tmp_bytes = h->prep_tmp.bytes;
+    CU(cub::DeviceScan::ExclusiveSum(h->prep_tmp.p, tmp_bytes, rowptr, rowptr, n + 1, h->stream));
+    int total = 0;
+    CU(cudaMemcpyAsync(&total, rowptr + n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    *out_nnz = total;
+    h->launches += 2;
+    if (total > capacity) return fail(h, SGRACE_EBOUNDS, "dense_to_csr: %d non-zeros, capacity %lld", total, (long long)capacity);
+    if (total == 0) return SGRACE_OK;
+    if (!col || !val) return fail(h, SGRACE_EINVAL, "dense_to_csr: col / val missing");
+    dense_fill_kernel<<<blocks, 256, 0, h->stream>>>(X, n, m, rowptr, capacity, col, val);
+    CU(cudaGetLastError());
+    h->launches++;
     return SGRACE_OK;
 }
 

@@ -66,6 +66,61 @@ def sym_norm2(edge_index, num_nodes, edge_weight=None, fill=0, dtype=None):
     return edge_index, deg_inv_sqrt[row] * edge_weight * deg_inv_sqrt[col]
 
 
+def _prep_handle(device):
+    """One library handle per device for the preparation calls (created on first use)."""
+    from . import _lib
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    h = _PREP_HANDLES.get(idx)
+    if h is None:
+        h = _PREP_HANDLES[idx] = _lib.Handle(idx)
+    h.set_stream(torch.cuda.current_stream(device).cuda_stream or 1)
+    return h
+
+
+_PREP_HANDLES = {}
+
+
+def sym_norm2_device(edge_index, num_nodes, edge_weight=None, fill=0, dtype=None):
+    """sym_norm2 on the GPU (`sgrace_sym_norm`): same signature, same values bit for bit, for CUDA tensors.
+    The reference runs this on the host before every forward."""
+    if not edge_index.is_cuda:
+        raise ValueError("sym_norm2_device needs CUDA tensors; sym_norm2 is the host version")
+    dev = edge_index.device
+    nnz = int(edge_index.size(1))
+    row = edge_index[0].to(torch.int32).contiguous()
+    col = edge_index[1].to(torch.int32).contiguous()
+    w = None if edge_weight is None else edge_weight.to(torch.float32).contiguous()
+    cap = nnz + int(num_nodes)
+    out_row = torch.empty(cap, dtype=torch.int32, device=dev)
+    out_col = torch.empty(cap, dtype=torch.int32, device=dev)
+    out_val = torch.empty(cap, dtype=torch.float32, device=dev)
+    h = _prep_handle(dev)
+    n = h.sym_norm(row.data_ptr(), col.data_ptr(), w.data_ptr() if w is not None else 0, nnz, int(num_nodes), float(fill), cap,
+                   out_row.data_ptr(), out_col.data_ptr(), out_val.data_ptr())
+    ei = torch.stack([out_row[:n], out_col[:n]]).to(edge_index.dtype)
+    return ei, out_val[:n]
+
+
+def to_sparse_device(x):
+    """CSR of a dense feature matrix on the GPU (`sgrace_dense_to_csr`): (rowptr, col, val) int32/int32/float32
+    CUDA tensors -- what `input.to_sparse()` feeds the accelerator buffers with (sgrace.py:1218-1227)."""
+    if not x.is_cuda:
+        raise ValueError("to_sparse_device needs a CUDA tensor")
+    x = x.to(torch.float32).contiguous()
+    n, m = x.shape
+    dev = x.device
+    h = _prep_handle(dev)
+    rowptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    cap = max(1, min(n * m, 1 << 20))
+    while True:
+        col = torch.empty(cap, dtype=torch.int32, device=dev)
+        val = torch.empty(cap, dtype=torch.float32, device=dev)
+        rc, nnz = h.dense_to_csr(x.data_ptr(), n, m, cap, rowptr.data_ptr(), col.data_ptr(), val.data_ptr())
+        if rc == 0:
+            return rowptr, col[:nnz], val[:nnz]
+        cap = nnz                      # SGRACE_EBOUNDS: the call reported the size it needs
+
+
 # ------------------------------------------------------------------------------------------
 # sgrace.py:267-294
 # ------------------------------------------------------------------------------------------
