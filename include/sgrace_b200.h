@@ -163,7 +163,7 @@ int sgrace_stage_times(sgrace_handle* h, float* fea_ms, float* adj_ms, float* to
 
 /* ---- direct call with device pointers: the argument list of mmult_top ---- */
 typedef struct {
-    int32_t gemm_mode;          /* 0 sparse X, 1 dense X (2 = hardware backward: unsupported) */
+    int32_t gemm_mode;          /* 0 sparse X, 1 dense X, 2 backward launch (float32 mode): D = values_adj[N_adj x M_adj, dense] . (CSR_fea[M_adj x M_fea] . W) */
     int32_t relu;
     int32_t gat_mode;           /* FULL mode only */
     int32_t N_adj, M_adj, M_fea, P_w;

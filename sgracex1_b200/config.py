@@ -8,7 +8,7 @@ hidden_channels = 16
 layer_count = 1          # layers processed per hardware call
 load_weights = 1
 
-accb = 0                 # accelerator in the backward path (not available: gemm_mode 2 is rejected)
+accb = 0                 # accelerator in the backward path (the mirror keeps the saved-tensor backward; gemm_mode 2 runs in float32 mode)
 acc = 1                  # accelerator in the forward path
 show_max_min = 0
 min_output = 1

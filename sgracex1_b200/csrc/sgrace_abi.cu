@@ -737,9 +737,16 @@ int run_adj(sgrace_handle* h, const sgrace_layer_desc* d, const int* rp_adj, con
 int check_desc(sgrace_handle* h, const sgrace_layer_desc* d) {
     if (!d) return fail(h, SGRACE_EINVAL, "null descriptor");
     if (d->N_adj < 0 || d->M_fea < 0 || d->P_w < 0) return fail(h, SGRACE_EINVAL, "negative dimension");
-    if (d->gemm_mode == 2)
-        return fail(h, SGRACE_EUNSUPPORTED,
-                    "gemm_mode=2 (hardware backward, sgrace.py:717) is not implemented; use the saved-tensor backward");
+    if (d->gemm_mode == 2) {
+        // the full design's backward launch (sgrace.py:717-760): dense "adjacency" operand, sparse "feature" operand
+        if (h->mode != SGRACE_MODE_F32_FAST)
+            return fail(h, SGRACE_EUNSUPPORTED,
+                        "gemm_mode=2 (hardware backward, sgrace.py:717) runs in the float32 mode only: the fixed-point "
+                        "arithmetic of that launch is not specified by the open sources");
+        if (d->M_adj < 0 || d->P_w % 4) return fail(h, SGRACE_EINVAL, "gemm_mode=2 needs M_adj >= 0 and P_w a multiple of 4");
+        if (h->index_format == 1 && d->nnz_fea < 0) return fail(h, SGRACE_EINVAL, "COO index format needs the non-zero count");
+        return 0;
+    }
     if (d->gemm_mode != 0 && d->gemm_mode != 1) return fail(h, SGRACE_EINVAL, "gemm_mode=%d", d->gemm_mode);
     if (h->index_format == 1 && ((d->gemm_mode == 0 && d->nnz_fea < 0) || d->nnz_adj < 0))
         return fail(h, SGRACE_EINVAL, "COO index format needs nnz_fea1 / nnz_adj1");
@@ -762,6 +769,30 @@ int layer_run_impl(sgrace_handle* h, const sgrace_layer_desc* d, bool timed) {
     }
     const int *rp_fea, *rp_adj;
     if (timed) CU(cudaEventRecord(h->ev[0], h->stream));
+    if (d->gemm_mode == 2) {
+        // D[N_adj x P] = act( Adense[N_adj x M_adj] . ( S[M_adj x M_fea] . W ) ):  grad_W = X^T (A g) with
+        // Adense = X^T, S = A, W = g (the B buffer holds g transposed, as always)
+        if (!d->values_adj || !d->D) return fail(h, SGRACE_EINVAL, "values_adj / D pointer not set");
+        sgrace_layer_desc f = *d;
+        f.gemm_mode = 0;
+        f.N_adj = d->M_adj;
+        if (int rc = ensure(h, h->xw, esz * (size_t)d->M_adj * (size_t)d->P_w + 16)) return rc;
+        XW = h->xw.p;
+        if (int rc = resolve_rowptrs(h, &f, &rp_fea, &rp_adj, true, false)) return rc;
+        if (int rc = run_fea(h, &f, rp_fea, XW)) return rc;
+        if (timed) CU(cudaEventRecord(h->ev[1], h->stream));
+        const int R = d->N_adj, K = d->M_adj, P4 = d->P_w / 4;
+        if (R > 0 && P4 > 0) {
+            if ((((uintptr_t)d->D) & 15) != 0) return fail(h, SGRACE_EINVAL, "gemm_mode=2 needs a 16-byte aligned D");
+            const long long warps = (long long)R * ((P4 + 31) / 32);
+            dense_adj_f32_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, h->stream>>>(
+                (const float*)d->values_adj, (const float4*)XW, (float4*)d->D, R, K, P4, d->relu != 0);
+            h->launches++;
+            CU(cudaGetLastError());
+        }
+        if (timed) CU(cudaEventRecord(h->ev[2], h->stream));
+        return 0;
+    }
     if (int rc = resolve_rowptrs(h, d, &rp_fea, &rp_adj, true, true)) return rc;
     // Small sparse-feature layers: one cooperative launch for the whole layer (W transpose | FEA | ADJ)
     if (h->mode == SGRACE_MODE_F32_FAST && d->gemm_mode == 0 && h->fused_small && d->N_adj > 0 && d->N_adj <= h->fused_small &&
@@ -1367,6 +1398,42 @@ int sgrace_start(sgrace_handle* h) {
 
     const size_t esz = elt_bytes(h->mode);
     const size_t N = (size_t)d.N_adj, M = (size_t)d.M_fea, P = (size_t)d.P_w;
+    if (d.gemm_mode == 2) {
+        // backward launch: the sparse operand (M_adj rows) sits behind the *_fea registers, the dense one
+        // (N_adj x M_adj) behind values_adj.  The driver does not rewrite the count registers for this launch
+        // (sgrace.py:717-790): in the COO format the count is the one the forward left in nnz_adj1.
+        const size_t R = (size_t)d.M_adj;
+        long long nnz = h->index_format == 1 ? (long long)d.nnz_adj : -1;
+        if (h->index_format == 0) {
+            size_t off;
+            const Buffer* b = find_buffer(h, a_rpf, &off);
+            if (b && off + (R + 1) * 4 > b->bytes) return fail(h, SGRACE_EBOUNDS, "rowPtr buffer too small for M_adj=%zu", R);
+            if (h->staging && b) nnz = ((const int*)((const char*)b->host + off))[R];
+            else if (d.rowPtr_fea && R) {
+                int v = 0;
+                CU(cudaMemcpyAsync(&v, d.rowPtr_fea + R, 4, cudaMemcpyDeviceToHost, h->stream));
+                CU(cudaStreamSynchronize(h->stream));
+                nnz = v;
+            }
+        }
+        if (nnz < 0) return fail(h, SGRACE_EBOUNDS, "negative non-zero count");
+        d.nnz_fea = (int32_t)nnz;
+        CU(cudaEventRecord(h->ev[4], h->stream));
+        if (h->staging) {
+            if (int rc = stage_in(h, a_rpf, h->index_format == 0 ? (R + 1) * 4 : (size_t)nnz * 4)) return rc;
+            if (int rc = stage_in(h, a_cif, (size_t)nnz * 4)) return rc;
+            if (int rc = stage_in(h, a_vf, (size_t)nnz * esz)) return rc;
+            if (int rc = stage_in(h, a_va, N * R * esz)) return rc;
+            if (int rc = stage_in(h, a_b, M * P * esz)) return rc;
+        }
+        h->ev_valid = false;
+        if (int rc = layer_run_impl(h, &d, true)) return rc;
+        if (h->staging) if (int rc = stage_out(h, a_d, N * P * esz)) return rc;
+        CU(cudaEventRecord(h->ev[3], h->stream));
+        h->ev_valid = true;
+        h->running = true;
+        return SGRACE_OK;
+    }
     // non-zero counts: registers (COO format) or the last row pointer read from the host mirror
     long long nnz_fea = d.nnz_fea, nnz_adj = d.nnz_adj;
     if (h->index_format == 0) {

@@ -366,6 +366,32 @@ fused_small_layer_f32_kernel(const int* __restrict__ rp_fea, const int* __restri
     }
 }
 
+// gemm_mode 2 (the full design's backward launch, sgrace.py:717-760): the ADJ operand is a dense
+// row-major matrix.  out[R x P] = act(A[R x K] . Bm[K x P]); one warp per output row and 128-column
+// block, the row of A is fetched 32 values at a time and broadcast by shuffle, k ascending.
+__global__ void __launch_bounds__(256)
+dense_adj_f32_kernel(const float* __restrict__ A, const float4* __restrict__ Bm, float4* __restrict__ out, int R, int K,
+                     int P4, int relu) {
+    const int lane = threadIdx.x & 31;
+    const int cblocks = (P4 + 31) / 32;
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= (long long)R * cblocks) return;
+    const int r = (int)(w / cblocks), q = (int)(w % cblocks) * 32 + lane;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        const float a = k0 + lane < K ? __ldg(A + (size_t)r * K + k0 + lane) : 0.f;
+        const int cnt = min(32, K - k0);
+        for (int j = 0; j < cnt; j++) {
+            const float aj = __shfl_sync(0xffffffffu, a, j);
+            if (q < P4 && aj != 0.f) fma4(acc, aj, Bm[(size_t)(k0 + j) * P4 + q]);
+        }
+    }
+    if (q < P4) {
+        if (relu) { acc.x = acc.x > 0.f ? acc.x : 0.f; acc.y = acc.y > 0.f ? acc.y : 0.f; acc.z = acc.z > 0.f ? acc.z : 0.f; acc.w = acc.w > 0.f ? acc.w : 0.f; }
+        out[(size_t)r * P4 + q] = acc;
+    }
+}
+
 __global__ void iota_u32_kernel(uint32_t* out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (uint32_t)i;

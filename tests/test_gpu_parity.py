@@ -311,7 +311,7 @@ def test_errors_are_reported(ip):
         with pytest.raises(_lib.SgraceError):
             hl.run()
         hl.columnIndex_adj[0] = adj[1][0]
-        ip.register_map.gemm_mode = 2                # hardware-backward mode: not part of this path
+        ip.register_map.gemm_mode = 3                # no such mode
         with pytest.raises(_lib.SgraceError):
             ip.register_map.CTRL.AP_START = 1
         ip.register_map.gemm_mode = 0
@@ -360,3 +360,78 @@ def test_dense_fea_tensor_core_path(ip, shape):
     ip.configure(dense_tc=1, staging=1, agg_first=0)
     # the two paths are different arithmetic (3xTF32 vs FMA) and must agree to float tolerance
     U.assert_close_f32(got[1][0], got[0][0], rtol=1e-5, what="tensor-core vs CUDA-core XW")
+
+
+# ------------------------------------------------------------------------------------------
+# the full design's backward launches (sgrace.py:717-880, `accb = 1`), float32 mode: grad_W through
+# gemm_mode 2 with the pointer re-wiring the reference's driver does, grad_X through gemm_mode 1
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("coo", [True, False])
+def test_backward_launches_gemm_mode_2_and_1(ip, coo):
+    from sgracex1_b200.pynq_compat import allocate
+    rng = np.random.default_rng(17)
+    n, m, p = 301, 52, 16
+    pr = U.random_problem(17, n=n, m=m, p=p, avg_deg=6)
+    rp, ci, va = pr["adj"]
+    nnz = len(ci)
+    x = (rng.random((n, m)) < 0.3).astype(np.float32) * rng.uniform(0.1, 1.0, size=(n, m)).astype(np.float32)
+    w = rng.uniform(-0.5, 0.5, size=(m, p)).astype(np.float32)
+    g = rng.standard_normal((n, p)).astype(np.float32)
+    A = np.zeros((n, n), np.float64)
+    A[np.repeat(np.arange(n), np.diff(rp)), ci] = 0          # duplicates accumulate below
+    np.add.at(A, (np.repeat(np.arange(n), np.diff(rp)), ci), va.astype(np.float64))
+    ip.configure(mode=_lib.MODE_F32_FAST, index_format=1 if coo else 0, staging=1)
+    al = lambda k, dt: allocate(max(int(k), 1), dtype=dt, target=ip)
+    rowPtr_adj, colIdx_adj, values_adj = al(max(nnz, n + 1), np.int32), al(nnz, np.int32), al(nnz, np.float32)
+    values_fea, B, D = al(n * max(m, p), np.float32), al(max(n, m) * p, np.float32), al(max(n, m) * max(m, p), np.float32)
+    rm = ip.register_map
+    try:
+        rowPtr_adj[:nnz if coo else n + 1] = np.repeat(np.arange(n, dtype=np.int32), np.diff(rp)) if coo else rp
+        colIdx_adj[:nnz] = ci
+        values_adj[:nnz] = va
+        rm.nnz_adj1 = nnz                                     # what the forward launch left behind
+        rm.B_offset_1 = B.physical_address
+        for i in "1234":
+            setattr(rm, f"D{i}_offset_1", D.physical_address)
+        # ---- grad_W = X^T (A g):  gemm_mode 2, adj loop <- X^T (dense), fea loop <- adjacency, B <- g^T ----
+        rm.gemm_mode, rm.relu, rm.gat_mode = 2, 0, 0
+        rm.N_adj, rm.M_adj, rm.M_fea, rm.P_w = m, n, n, p
+        values_fea[:m * n] = x.T.reshape(-1)
+        B[:n * p] = g.T.reshape(-1)
+        for i in "1234":
+            setattr(rm, f"values_adj{i}_offset_1", values_fea.physical_address)
+            setattr(rm, f"values_fea{i}_offset_1", values_adj.physical_address)
+            setattr(rm, f"rowPtr_fea{i}_offset_1", rowPtr_adj.physical_address)
+            setattr(rm, f"columnIndex_fea{i}_offset_1", colIdx_adj.physical_address)
+        rm.CTRL.AP_START = 1
+        while rm.CTRL.AP_DONE == 0:
+            pass
+        ip.handle.wait()
+        grad_w = np.array(D[:m * p]).reshape(m, p)
+        U.assert_close_f32(grad_w, x.T.astype(np.float64) @ (A @ g.astype(np.float64)), what="grad_W through gemm_mode 2")
+        # ---- grad_X = A (g W^T):  gemm_mode 1, fea loop <- g (dense), B <- W as stored (M x P) ----
+        rm.gemm_mode = 1
+        rm.N_adj, rm.M_adj, rm.M_fea, rm.P_w = n, n, p, m
+        values_fea[:n * p] = g.reshape(-1)
+        B[:m * p] = w.reshape(-1)
+        for i in "1234":
+            setattr(rm, f"values_adj{i}_offset_1", values_adj.physical_address)
+            setattr(rm, f"rowPtr_adj{i}_offset_1", rowPtr_adj.physical_address)
+            setattr(rm, f"columnIndex_adj{i}_offset_1", colIdx_adj.physical_address)
+            setattr(rm, f"values_fea{i}_offset_1", values_fea.physical_address)
+        rm.CTRL.AP_START = 1
+        while rm.CTRL.AP_DONE == 0:
+            pass
+        ip.handle.wait()
+        grad_x = np.array(D[:n * m]).reshape(n, m)
+        U.assert_close_f32(grad_x, A @ (g.astype(np.float64) @ w.T.astype(np.float64)), what="grad_X through gemm_mode 1")
+        # the fixed-point designs do not specify this launch: reported, not guessed
+        ip.configure(mode=_lib.MODE_FULL)
+        rm.gemm_mode = 2
+        with pytest.raises(_lib.SgraceError):
+            rm.CTRL.AP_START = 1
+    finally:
+        rm.gemm_mode = 0
+        ip.configure(mode=_lib.MODE_F32_FAST, index_format=0)
+        for b in (rowPtr_adj, colIdx_adj, values_adj, values_fea, B, D):
+            b.freebuffer()
