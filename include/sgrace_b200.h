@@ -82,6 +82,8 @@ enum {
     SGRACE_OPT_DENSE_TC = 14,       /* 1: allow the tcgen05 path for wide dense FEA (FAST)  */
     SGRACE_OPT_STREAM_KERNEL = 15,  /* 1 (default): TMA-staged persistent SpMM kernel (FAST);
                                        0: the row-strided kernel (any pointer alignment)    */
+    SGRACE_OPT_ROW_OFFSET = 19,     /* row-partitioned GAT (sgrace_adj_run on a slice of the adjacency rows against the
+                                       full feature-stage result): global index of the slice's first row; default 0 */
     SGRACE_OPT_FUSED_SMALL = 18,    /* sparse-feature FAST layers with at most this many rows run as ONE cooperative
                                        launch (W transpose | FEA | ADJ with grid barriers); default 65536, 0 = off */
     SGRACE_OPT_ACCUMULATE = 17,     /* 1: the ADJ stage computes D = act(D + A.XW): the second pass over an

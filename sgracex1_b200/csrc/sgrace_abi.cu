@@ -50,6 +50,7 @@ struct sgrace_handle {
     int mode = SGRACE_MODE_F32_FAST;
     int spmm_block = 1, lat_fea = 0, lat_adj = 0, fea_threads = 1, adj_threads = 1, use_sblocks = 0;
     int index_format = 0, qbits = 8, staging = 1, long_row = 512, validate = 0, dense_tc = 1, stream_kernel = 1, agg_first = 0, accumulate = 0;
+    int row_offset = 0;                         // global index of the ADJ stage's local row 0 (row-partitioned GAT)
     int fused_small = 65536;                    // layers with at most this many rows run as one cooperative launch (0: off)
     unsigned counter_phase = 0;                 // which of the two counter sets the next SpMM launch uses
     // set for the duration of sgrace_adj_run_peer
@@ -692,6 +693,8 @@ int run_adj(sgrace_handle* h, const sgrace_layer_desc* d, const int* rp_adj, con
                 return 0;
             }
             if (!d->attention) return fail(h, SGRACE_EINVAL, "gat_mode set but ate_m (attention) pointer missing");
+            if (h->row_offset < 0 || (long long)h->row_offset + N > xw_rows)
+                return fail(h, SGRACE_EINVAL, "row_offset %d + N_adj %d exceeds the %d rows of the feature-stage result", h->row_offset, N, xw_rows);
             if (int rc = ensure(h, h->s1, sizeof(float) * (size_t)xw_rows)) return rc;
             if (int rc = ensure(h, h->s2, sizeof(float) * (size_t)xw_rows)) return rc;
             if (int rc = ensure(h, h->lists, sizeof(int) * (size_t)N)) return rc;
@@ -706,7 +709,7 @@ int run_adj(sgrace_handle* h, const sgrace_layer_desc* d, const int* rp_adj, con
                 CU(cudaGetLastError());
 #define SGRACE_GATQ(L, V) gat_aggregate_vec_kernel<L, V><<<(unsigned)(((long long)N * L + 255) / 256), 256, 0, h->stream>>>( \
                     rp_adj, d->columnIndex_adj, (const float*)d->values_adj, (const float4*)XW, (const float*)h->s1.p,       \
-                    (const float*)h->s2.p, (float4*)d->D, d->E, d->S, N, P4, relu, quant, qc, (int*)h->lists.p, empty_count)
+                    (const float*)h->s2.p, (float4*)d->D, d->E, d->S, N, P4, relu, quant, qc, (int*)h->lists.p, empty_count, h->row_offset)
                 SGRACE_P4_DISPATCH(P4, SGRACE_GATQ);
 #undef SGRACE_GATQ
             } else {
@@ -719,7 +722,7 @@ int run_adj(sgrace_handle* h, const sgrace_layer_desc* d, const int* rp_adj, con
                 gat_aggregate_kernel<<<grid, 256, 0, h->stream>>>(rp_adj, d->columnIndex_adj, (const float*)d->values_adj,
                                                                   (const float*)XW, (const float*)h->s1.p,
                                                                   (const float*)h->s2.p, (float*)d->D, d->E, d->S, N, P,
-                                                                  relu, quant, qc, (int*)h->lists.p, empty_count);
+                                                                  relu, quant, qc, (int*)h->lists.p, empty_count, h->row_offset);
             }
             h->launches++;
             CU(cudaGetLastError());
@@ -1092,6 +1095,7 @@ int sgrace_set_option(sgrace_handle* h, int key, int64_t v) {
         case SGRACE_OPT_AGG_FIRST: h->agg_first = v != 0; break;
         case SGRACE_OPT_ACCUMULATE: h->accumulate = v != 0; break;
         case SGRACE_OPT_FUSED_SMALL: if (v < 0) return fail(h, SGRACE_EINVAL, "fused_small < 0"); h->fused_small = (int)v; break;
+        case SGRACE_OPT_ROW_OFFSET: if (v < 0) return fail(h, SGRACE_EINVAL, "row_offset < 0"); h->row_offset = (int)v; break;
         default: return fail(h, SGRACE_EINVAL, "unknown option %d", key);
     }
     return SGRACE_OK;
@@ -1118,6 +1122,7 @@ int sgrace_get_option(sgrace_handle* h, int key, int64_t* v) {
         case SGRACE_OPT_AGG_FIRST: *v = h->agg_first; break;
         case SGRACE_OPT_ACCUMULATE: *v = h->accumulate; break;
         case SGRACE_OPT_FUSED_SMALL: *v = h->fused_small; break;
+        case SGRACE_OPT_ROW_OFFSET: *v = h->row_offset; break;
         default: return fail(h, SGRACE_EINVAL, "unknown option %d", key);
     }
     return SGRACE_OK;

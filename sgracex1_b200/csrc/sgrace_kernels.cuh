@@ -1092,13 +1092,13 @@ gat_aggregate_kernel(const int* __restrict__ rowptr, const int* __restrict__ col
                      const float* __restrict__ s1, const float* __restrict__ s2,
                      float* __restrict__ out, float* __restrict__ E, float* __restrict__ S,
                      int nrows, int P, int relu, int quant, QConst qc,
-                     int* __restrict__ empty_rows, int* __restrict__ empty_count) {
+                     int* __restrict__ empty_rows, int* __restrict__ empty_count, int row0) {
     const int lane = threadIdx.x & 31;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long row = warp0; row < nrows; row += nwarps) {
         const int beg = rowptr[row], end = rowptr[row + 1];
-        const float si = s1[row];
+        const float si = s1[row0 + row];          // row0: global index of local row 0 (row-partitioned GAT)
         float mx = -INFINITY;
         int live = 0;
         for (int k = beg + lane; k < end; k += 32) {
@@ -1281,14 +1281,14 @@ __global__ void __launch_bounds__(256)
 gat_aggregate_vec_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ val,
                          const float4* __restrict__ Wh, const float* __restrict__ s1, const float* __restrict__ s2,
                          float4* __restrict__ out, float* __restrict__ E, float* __restrict__ S, int nrows, int P4,
-                         int relu, int quant, QConst qc, int* __restrict__ empty_rows, int* __restrict__ empty_count) {
+                         int relu, int quant, QConst qc, int* __restrict__ empty_rows, int* __restrict__ empty_count, int row0) {
     constexpr int RPW = 32 / LPR;
     const int lane = threadIdx.x & 31, g = lane / LPR, l = lane % LPR;
     const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (g * LPR));
     const long long row = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * RPW + g;
     if (row >= nrows) return;
     const int beg = rowptr[row], end = rowptr[row + 1];
-    const float si = s1[row];
+    const float si = s1[row0 + row];              // row0: global index of local row 0 (row-partitioned GAT)
     // logits, row maximum, surviving-edge count
     float mx = -INFINITY;
     int live = 0;

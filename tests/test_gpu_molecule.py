@@ -273,3 +273,63 @@ def test_halo_layer_copy_engine_exchange_three_emulated_ranks(monkeypatch):
             U.assert_close_f32(out.cpu().numpy(), want[lo:hi], what=f"dma halo layer rank {r} rep {rep}")
     for hm, _ in handles:
         hm.peer_release()
+
+
+def test_quantised_gat_layer_row_partition_two_emulated_ranks():
+    """SURVEY 8e for the full design: FEA on each rank's rows into its slot of the gathered Wh, then the GAT
+    stage on the local adjacency rows against the full Wh (the scores are recomputed from it).  Per-row work
+    is deterministic, so every rank's D / E / S must equal the one-GPU layer bit for bit."""
+    from oracle import oracle as O
+    from sgracex1_b200 import quant as Q
+    n, m, p, world = 600, 48, 16, 2
+    pr = U.random_problem(31, n=n, m=m, p=p, avg_deg=5)
+    rp, ci, va = pr["adj"]
+    va = np.abs(va).astype(np.float32)
+    frp, fci, fva = pr["fea"]
+    fva = np.abs(fva).astype(np.float32)
+    c = Q.layer_constants(8)
+    att = np.random.default_rng(3).uniform(-0.5, 0.5, size=2 * p).astype(np.float32)
+    dev = torch.device("cuda:0")
+    h = _lib.Handle(0)
+    for k, v in ((_lib.OPT_MODE, _lib.MODE_FULL), (_lib.OPT_QBITS, 8), (_lib.OPT_STAGING, 0), (_lib.OPT_INDEX_FORMAT, 0)):
+        h.set_option(k, v)
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    Bd, attd = up(O.weights_to_B(pr["W"]).astype(np.float32)), up(att)
+
+    def desc(fea, adj, n_rows, D, E, S, XW=None):
+        d = _lib.LayerDesc()
+        d.gemm_mode, d.relu, d.gat_mode = 0, 1, 1
+        d.N_adj, d.M_adj, d.M_fea, d.P_w = n_rows, n, m, p
+        d.scale_fea, d.internal_quantization = c["scale_fea"], c["internal_quantization"]
+        d.qscale_fea, d.qscale_w, d.qscale_adj, d.deq_factor = 1 / c["f_s"], 1 / c["w_s"], 1 / c["a_s"], c["deq_o"]
+        d.rowPtr_fea, d.columnIndex_fea, d.values_fea = (t.data_ptr() for t in fea)
+        d.rowPtr_adj, d.columnIndex_adj, d.values_adj = (t.data_ptr() for t in adj)
+        d.nnz_fea, d.nnz_adj = int(fea[1].numel()), int(adj[1].numel())
+        d.B, d.attention, d.D, d.E, d.S = Bd.data_ptr(), attd.data_ptr(), D.data_ptr(), E.data_ptr(), S.data_ptr()
+        if XW is not None:
+            d.XW = XW.data_ptr()
+        return d
+
+    fea_full, adj_full = tuple(up(a) for a in (frp, fci, fva)), tuple(up(a) for a in (rp, ci, va))
+    D0, E0, S0 = torch.empty(n, p, device=dev), torch.empty(len(ci), device=dev), torch.empty(len(ci), device=dev)
+    h.layer_run(desc(fea_full, adj_full, n, D0, E0, S0))
+    h.wait()
+    Wh = torch.zeros(n, p, device=dev)            # the all-gathered buffer; each rank fills its slot
+    parts = []
+    for r in range(world):
+        lo, hi = sdist.row_range(n, r, world)
+        fea_loc = tuple(up(a) for a in sdist.csr_row_slice(frp, fci, fva, lo, hi))
+        adj_loc = tuple(up(a) for a in sdist.csr_row_slice(rp, ci, va, lo, hi))
+        D, E, S = torch.empty(hi - lo, p, device=dev), torch.empty(adj_loc[1].numel(), device=dev), torch.empty(adj_loc[1].numel(), device=dev)
+        d = desc(fea_loc, adj_loc, hi - lo, D, E, S)
+        h.fea_run(d, Wh.data_ptr() + lo * p * 4)
+        parts.append((lo, hi, d, D, E, S, fea_loc, adj_loc))
+    for lo, hi, d, D, E, S, _, _ in parts:          # after the "all-gather": every slot is filled
+        h.set_option(_lib.OPT_ROW_OFFSET, lo)       # the destination row's own score is read at its global index
+        h.adj_run(d, Wh.data_ptr(), n)
+    h.set_option(_lib.OPT_ROW_OFFSET, 0)
+    h.wait()
+    for lo, hi, d, D, E, S, _, _ in parts:
+        assert torch.equal(D, D0[lo:hi]), f"rows {lo}:{hi}"
+        assert torch.equal(E, E0[rp[lo]:rp[hi]]) and torch.equal(S, S0[rp[lo]:rp[hi]])
+    assert float(D0.abs().sum()) > 0
