@@ -172,3 +172,42 @@ def test_split_by_ownership_reassembles_the_adjacency():
             for r in range(hi - lo):
                 got[r] += v2[r2[r]:r2[r + 1]] @ buf[c2[r2[r]:r2[r + 1]]]
         np.testing.assert_allclose(got, want[lo:hi], rtol=1e-5, atol=1e-6)
+
+
+def test_halo_push_lists_fill_every_halo_slot_in_order():
+    """The exchange bookkeeping of HaloLayer without a GPU: what every rank asks for (`_halo_wants`), turned into
+    the owners' push lists (`_exchange_push_lists`), must deliver exactly the rows each rank's halo slots name,
+    in slot order -- simulated with numpy copies in place of the copy engines."""
+    world, n, width = 3, 1000, 4
+    rng = np.random.default_rng(9)
+    deg = rng.integers(1, 9, size=n)
+    rp = np.zeros(n + 1, np.int32)
+    np.cumsum(deg, out=rp[1:])
+    ci = rng.integers(0, n, size=int(rp[-1])).astype(np.int32)
+    va = np.ones(len(ci), np.float32)
+    x = rng.standard_normal((n, width)).astype(np.float32)
+    block = sdist.row_block(n, world)
+    layers = []
+    for r in range(world):
+        lo, hi = sdist.row_range(n, r, world)
+        lay = object.__new__(sdist.HaloLayer)            # the bookkeeping only: no device buffers
+        lay.rank, lay.world, lay.block, lay.lo, lay.hi, lay.width = r, world, block, lo, hi, width
+        loc = sdist.csr_row_slice(rp, ci, va, lo, hi)
+        _, _, lay.halo_rows_np = sdist.split_by_ownership(*loc, lo, hi, block)
+        lay.n_halo = len(lay.halo_rows_np)
+        lay.bases = [10_000_000 * (q + 1) for q in range(world)]      # fake base addresses, one region per rank
+        layers.append(lay)
+    wants = [lay._halo_wants(lay.halo_rows_np)[1] for lay in layers]
+    halos = [np.full((lay.n_halo, width), np.nan, np.float32) for lay in layers]
+    for lay in layers:
+        lay._exchange_push_lists(lay.halo_rows_np, "cpu", gather=lambda w: wants)
+        rows_t, counts, dsts = lay.push
+        assert sum(lay.a2a["in_splits"]) == sum(counts)
+        for dest, rows, cnt, dst in zip(lay.push_ranks, rows_t, counts, dsts):
+            slot0 = (dst - layers[dest].bases[dest]) // (width * 4) - block      # first halo slot this owner fills
+            assert (dst - layers[dest].bases[dest]) % (width * 4) == 0 and 0 <= slot0 <= layers[dest].n_halo - cnt
+            halos[dest][slot0:slot0 + cnt] = x[lay.lo + rows.numpy()]
+    for lay, halo in zip(layers, halos):
+        assert not np.isnan(halo).any()
+        assert np.array_equal(halo, x[lay.halo_rows_np])
+        assert lay.a2a["out_splits"][lay.rank] == 0 and sum(lay.a2a["out_splits"]) == lay.n_halo
