@@ -465,6 +465,214 @@ class HaloLayer:
 
 
 # ------------------------------------------------------------------------------------------
+# pipelined halo exchange: the local rows are cut into chunks, every remote row is
+# assigned to the first chunk that references it, and the halo travels chunk by chunk so that the remote pass and
+# the dense stage of chunk c run under the transfer of chunk c+1.  Opt-in (SGRACE_HALO_CHUNKS > 1).
+# ------------------------------------------------------------------------------------------
+def plan_halo_chunks(rowptr, col, val, lo, hi, block, n_chunks):
+    """Host-side plan for one rank.  Returns a dict with
+         cuts         int64[n_chunks + 1]   local row cuts (equal row counts)
+         halo_rows    int32[n_halo]         remote global row ids ordered by (first referencing chunk, id)
+         chunk_slots  int64[n_chunks + 1]   halo slot range of every chunk
+         a_loc        CSR over all local rows, owned columns only, columns = local row index
+         a_rem        one CSR per chunk over the chunk's rows, remote columns only, columns = block + halo slot"""
+    rowptr, col, val = np.asarray(rowptr), np.asarray(col).astype(np.int64), np.asarray(val)
+    n = len(rowptr) - 1
+    cuts = (np.arange(n_chunks + 1, dtype=np.int64) * n) // n_chunks
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(rowptr))
+    own = (col >= lo) & (col < hi)
+
+    def csr(r0, r1, mask, newcol):
+        rp = np.zeros(r1 - r0 + 1, np.int32)
+        np.cumsum(np.bincount(rows[mask] - r0, minlength=r1 - r0), out=rp[1:])
+        return rp, newcol.astype(np.int32), val[mask]
+
+    a_loc = csr(0, n, own, col[own] - lo)
+    rem = ~own
+    chunk_of_entry = np.searchsorted(cuts, rows, side="right") - 1
+    ids, inv = np.unique(col[rem], return_inverse=True)
+    first = np.full(len(ids), n_chunks, np.int64)
+    np.minimum.at(first, inv, chunk_of_entry[rem])
+    order = np.lexsort((ids, first))
+    halo_rows = ids[order].astype(np.int32)
+    slot_of_id = np.empty(len(ids), np.int64)
+    slot_of_id[order] = np.arange(len(ids))
+    chunk_slots = np.searchsorted(first[order], np.arange(n_chunks + 1)).astype(np.int64)
+    slot_of_entry = np.zeros(len(col), np.int64)
+    slot_of_entry[rem] = slot_of_id[inv]
+    a_rem = []
+    for c in range(n_chunks):
+        m = rem & (chunk_of_entry == c)
+        a_rem.append(csr(int(cuts[c]), int(cuts[c + 1]), m, block + slot_of_entry[m]))
+    return dict(cuts=cuts, halo_rows=halo_rows, chunk_slots=chunk_slots, a_loc=a_loc, a_rem=a_rem)
+
+
+def chunk_wants(plan, rank, world, block):
+    """{owner: [(first halo slot, global row ids) per chunk]}: what this rank needs, chunk by chunk."""
+    want = {o: [] for o in range(world) if o != rank}
+    halo_rows, cs = plan["halo_rows"], plan["chunk_slots"]
+    for c in range(len(cs) - 1):
+        seg = halo_rows[cs[c]:cs[c + 1]]
+        bounds = np.searchsorted(seg, [o * block for o in range(world + 1)])
+        for o in want:
+            want[o].append((int(cs[c] + bounds[o]), seg[bounds[o]:bounds[o + 1]]))
+    return want
+
+
+def chunk_push_lists(all_wants, rank, lo, n_chunks):
+    """What this rank sends: [chunk][k] = (destination rank, first halo slot there, LOCAL row indices), destinations in
+    ring order (rank+1, rank+2, ...) so that every step of the exchange is a permutation."""
+    world = len(all_wants)
+    out = []
+    for c in range(n_chunks):
+        lst = []
+        for step in range(1, world):
+            r = (rank + step) % world
+            slot0, ids = all_wants[r][rank][c]
+            if len(ids):
+                lst.append((r, slot0, (np.asarray(ids, np.int64) - lo).astype(np.int32)))
+        out.append(lst)
+    return out
+
+
+class ChunkedHaloLayer:
+    """HaloLayer with the exchange pipelined over row chunks (see plan_halo_chunks).  Same contract as
+    HaloLayer.forward; only the copy-engine exchange.  Streams: main (pack, aggregation, dense), send (copies and
+    flag writes), wait (stream waits on this rank's flags -- separate from `send`, whose copies of the later chunks
+    would otherwise sit in front of the waits for the earlier ones)."""
+
+    def __init__(self, handle_main, adj_local_np, n_rows, width, rank, world, device, n_chunks, exchange=None, gather=None):
+        import torch
+        from . import _lib
+        if n_chunks * world > 64:
+            raise ValueError("chunks x ranks exceeds the 64 flag words")
+        self.hm, self.N, self.width, self.rank, self.world, self.n_chunks = handle_main, n_rows, width, rank, world, n_chunks
+        self.block = row_block(n_rows, world)
+        self.lo, self.hi = row_range(n_rows, rank, world)
+        self.plan = plan = plan_halo_chunks(*adj_local_np, self.lo, self.hi, self.block, n_chunks)
+        self.n_halo = int(len(plan["halo_rows"]))
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+        self.a_loc = tuple(up(a) for a in plan["a_loc"])
+        self.a_rem = [tuple(up(a) for a in t) for t in plan["a_rem"]]
+        addr, ipc = handle_main.peer_alloc((self.block + max(self.n_halo, 1)) * width * 4)
+        self.addr = addr
+        self.flag_addr, flag_ipc = handle_main.peer_alloc(256)
+        torch.as_tensor(_RawCuda(self.flag_addr, (64,), "<i4"), device=device).zero_()
+        self.epoch = 0
+        if exchange is None:
+            def exchange(mine):
+                out = [None] * world
+                dist.all_gather_object(out, mine)
+                return out
+        if exchange == "defer":
+            self.bases = self.flag_bases = None
+        else:
+            handles = exchange((ipc, flag_ipc))
+            self.bases = [addr if r == rank else handle_main.peer_open(handles[r][0]) for r in range(world)]
+            self.flag_bases = [self.flag_addr if r == rank else handle_main.peer_open(handles[r][1]) for r in range(world)]
+        self.buf = torch.as_tensor(_RawCuda(addr, (self.block + max(self.n_halo, 1), width)), device=device)
+        self.buf.zero_()
+        self.local = self.buf[:self.block]
+        self.wants = chunk_wants(plan, rank, world, self.block)
+        self.push = None
+        if exchange != "defer":
+            self.set_push_lists((gather or exchange)(self.wants), device)
+        self.s_main = torch.cuda.current_stream(device)
+        self.lanes = []
+        for _ in range(2):                       # send, wait
+            hx, sx = _lib.Handle(device.index or 0), torch.cuda.Stream(device)
+            hx.set_option(_lib.OPT_STAGING, 0)
+            hx.set_stream(sx.cuda_stream)
+            self.lanes.append((hx, sx))
+        self.ev_ready, self.ev_sent = torch.cuda.Event(), torch.cuda.Event()
+        self.ev_chunk = [torch.cuda.Event() for _ in range(n_chunks)]
+
+    def set_push_lists(self, all_wants, device):
+        import torch
+        lists = chunk_push_lists(all_wants, self.rank, self.lo, self.n_chunks)
+        total = sum(len(rows) for lst in lists for _, _, rows in lst)
+        self.send = torch.empty(max(total, 1), self.width, dtype=torch.float32, device=device)
+        self.push, off = [], 0
+        for lst in lists:
+            entries = []
+            for r, slot0, rows in lst:
+                entries.append(dict(dest=r, rows=torch.from_numpy(rows).to(device), count=len(rows), src_off=off * self.width * 4,
+                                    dst=self.bases[r] + (self.block + slot0) * self.width * 4))
+                off += len(rows)
+            self.push.append(entries)
+
+    def _adj(self, adj, out_ptr, accumulate):
+        from . import _lib
+        rp, ci, va = adj
+        n = rp.numel() - 1
+        if n == 0:
+            return
+        d = _lib.LayerDesc()
+        d.N_adj, d.M_adj, d.P_w, d.relu = n, self.buf.shape[0], self.width, 0
+        d.rowPtr_adj, d.columnIndex_adj, d.values_adj = rp.data_ptr(), ci.data_ptr(), va.data_ptr()
+        d.nnz_adj = int(ci.numel())
+        d.D = out_ptr
+        self.hm.set_option(_lib.OPT_ACCUMULATE, 1 if accumulate else 0)
+        try:
+            self.hm.adj_run(d, self.buf.data_ptr(), self.buf.shape[0])
+        finally:
+            self.hm.set_option(_lib.OPT_ACCUMULATE, 0)
+
+    def forward_begin(self):
+        import torch
+        n = self.hi - self.lo
+        t = torch.empty(n, self.width, dtype=torch.float32, device=self.buf.device)
+        (h_send, s_send), _ = self.lanes
+        self.s_main.wait_event(self.ev_sent)             # the send buffer of the previous layer has drained
+        for entries in self.push:                        # pack on the main stream, one launch per chunk (<= 8 destinations)
+            if entries:
+                self.hm.halo_push(self.local.data_ptr(), self.width, [e["rows"].data_ptr() for e in entries],
+                                  [e["count"] for e in entries], [self.send.data_ptr() + e["src_off"] for e in entries])
+        self.ev_ready.record(self.s_main)
+        s_send.wait_event(self.ev_ready)
+        self.epoch += 1
+        for c, entries in enumerate(self.push):
+            by_dest = {e["dest"]: e for e in entries}
+            for step in range(1, self.world):
+                r = (self.rank + step) % self.world
+                e = by_dest.get(r)
+                if e is not None:
+                    h_send.peer_copy(e["dst"], self.send.data_ptr() + e["src_off"], e["count"] * self.width * 4)
+                h_send.peer_signal(self.flag_bases[r] + 4 * (c * self.world + self.rank), self.epoch)
+        self.ev_sent.record(s_send)
+        self._adj(self.a_loc, t.data_ptr(), False)
+        return t
+
+    def forward_end(self, t, W, relu):
+        import torch
+        n = self.hi - self.lo
+        _, (h_wait, s_wait) = self.lanes
+        M, P = W.shape
+        Bt = W.t().contiguous()
+        out = torch.empty(n, P, dtype=torch.float32, device=t.device)
+        cuts = self.plan["cuts"]
+        for c in range(self.n_chunks):
+            for r in range(self.world):
+                if r != self.rank:
+                    h_wait.wait_flag(self.flag_addr + 4 * (c * self.world + r), self.epoch)
+            self.ev_chunk[c].record(s_wait)
+        for c in range(self.n_chunks):
+            r0, r1 = int(cuts[c]), int(cuts[c + 1])
+            if r1 == r0:
+                continue
+            self.s_main.wait_event(self.ev_chunk[c])
+            self._adj(self.a_rem[c], t.data_ptr() + r0 * self.width * 4, True)
+            self.hm.dense_run(t.data_ptr() + r0 * self.width * 4, Bt.data_ptr(), out.data_ptr() + r0 * P * 4, r1 - r0, M, P, relu)
+        return out, (t, Bt)
+
+    def forward(self, W, relu, timing=None):
+        return self.forward_end(self.forward_begin(), W, relu)
+
+    def release(self):
+        self.hm.peer_release()
+
+
+# ------------------------------------------------------------------------------------------
 # bench.py --workload products
 # ------------------------------------------------------------------------------------------
 def bench_products(args):
@@ -514,7 +722,11 @@ def bench_products(args):
         handle2 = _lib.Handle(local)
         handle2.set_option(_lib.OPT_MODE, _lib.MODE_F32_FAST)
         handle2.set_option(_lib.OPT_STAGING, 0)
-        layer = HaloLayer(handle, handle2, (rp, ci, va), N, M, rank, world, dev)
+        n_chunks = int(os.environ.get("SGRACE_HALO_CHUNKS", "1"))
+        if n_chunks > 1:      # opt-in: exchange pipelined over row chunks (not yet the default: unmeasured)
+            layer = ChunkedHaloLayer(handle, (rp, ci, va), N, M, rank, world, dev, n_chunks)
+        else:
+            layer = HaloLayer(handle, handle2, (rp, ci, va), N, M, rank, world, dev)
         layer.local[:hi - lo].copy_(x_local)
         exchanged = int(layer.n_halo * M * 4)
         barrier()

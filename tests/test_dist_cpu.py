@@ -6,6 +6,7 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -211,3 +212,60 @@ def test_halo_push_lists_fill_every_halo_slot_in_order():
         assert not np.isnan(halo).any()
         assert np.array_equal(halo, x[lay.halo_rows_np])
         assert lay.a2a["out_splits"][lay.rank] == 0 and sum(lay.a2a["out_splits"]) == lay.n_halo
+
+
+@pytest.mark.parametrize("n_chunks", [1, 2, 4])
+def test_chunked_halo_plan_reassembles_the_layer(n_chunks):
+    """plan_halo_chunks / chunk_wants / chunk_push_lists (the pipelined exchange, host side): with the pushes of
+    chunks 0..c delivered, the owned pass plus the remote pass of chunk c must give the rows of chunk c of A.X --
+    i.e. a chunk never reads a halo slot that arrives later."""
+    world, n, width = 3, 900, 5
+    rng = np.random.default_rng(21)
+    deg = rng.integers(0, 10, size=n)
+    rp = np.zeros(n + 1, np.int32)
+    np.cumsum(deg, out=rp[1:])
+    ci = rng.integers(0, n, size=int(rp[-1])).astype(np.int32)
+    va = rng.uniform(-1, 1, size=len(ci)).astype(np.float32)
+    x = rng.standard_normal((n, width)).astype(np.float64)
+    A = np.zeros((n, n))
+    np.add.at(A, (np.repeat(np.arange(n), deg), ci), va.astype(np.float64))
+    want = A @ x
+    block = sdist.row_block(n, world)
+    plans, wants = [], []
+    for r in range(world):
+        lo, hi = sdist.row_range(n, r, world)
+        plans.append(sdist.plan_halo_chunks(*sdist.csr_row_slice(rp, ci, va, lo, hi), lo, hi, block, n_chunks))
+        wants.append(sdist.chunk_wants(plans[-1], r, world, block))
+    pushes = [sdist.chunk_push_lists(wants, r, sdist.row_range(n, r, world)[0], n_chunks) for r in range(world)]
+
+    def dense(csr, ncols):
+        crp, cci, cva = csr
+        m = np.zeros((len(crp) - 1, ncols))
+        np.add.at(m, (np.repeat(np.arange(len(crp) - 1), np.diff(crp)), cci), cva.astype(np.float64))
+        return m
+
+    for r in range(world):
+        lo, hi = sdist.row_range(n, r, world)
+        plan = plans[r]
+        n_halo = len(plan["halo_rows"])
+        assert plan["chunk_slots"][0] == 0 and plan["chunk_slots"][-1] == n_halo
+        buf = np.full((block + n_halo, width), np.nan)
+        buf[:hi - lo] = x[lo:hi]
+        buf[hi - lo:block] = 0.0
+        t = dense(plan["a_loc"], block + n_halo)[:, :block] @ np.nan_to_num(buf[:block])
+        for c in range(n_chunks):
+            for s in range(world):                          # deliver what every owner sends for chunk c
+                if s == r:
+                    continue
+                slo = sdist.row_range(n, s, world)[0]
+                for dest, slot0, rows in pushes[s][c]:
+                    if dest == r:
+                        assert plan["chunk_slots"][c] <= slot0 and slot0 + len(rows) <= plan["chunk_slots"][c + 1]
+                        buf[block + slot0:block + slot0 + len(rows)] = x[slo + rows]
+            r0, r1 = int(plan["cuts"][c]), int(plan["cuts"][c + 1])
+            rem = dense(plan["a_rem"][c], block + n_halo)
+            used = np.abs(rem).sum(axis=0) > 0
+            assert not np.isnan(buf[used]).any(), f"rank {r} chunk {c} reads a halo slot that has not arrived"
+            got = t[r0:r1] + rem @ np.nan_to_num(buf)
+            np.testing.assert_allclose(got, want[lo + r0:lo + r1], rtol=1e-9, atol=1e-9)
+        assert not np.isnan(buf[block:]).any() and np.array_equal(buf[block:], x[plan["halo_rows"]])
