@@ -204,7 +204,8 @@ int sgrace_dense_run(sgrace_handle* h, const void* X, const void* B, void* out, 
  * addresses, its own included.  No all-gather: only the rows an adjacency row references move. */
 int sgrace_peer_alloc(sgrace_handle* h, size_t bytes, uint64_t* device_addr, unsigned char handle_out[64]);
 int sgrace_peer_open(sgrace_handle* h, const unsigned char handle_in[64], uint64_t* device_addr);
-int sgrace_peer_release(sgrace_handle* h);     /* closes every mapping and frees every peer buffer of h */
+int sgrace_peer_close(sgrace_handle* h);       /* closes every mapping h imported (call on every rank, then barrier) */
+int sgrace_peer_release(sgrace_handle* h);     /* closes the remaining mappings and frees every peer buffer h exported */
 int sgrace_adj_run_peer(sgrace_handle* h, const sgrace_layer_desc* d, const uint64_t* bases, int32_t n_peers,
                         int32_t block_rows);
 /* halo exchange: copy `n_rows` listed rows (global row ids, int32, device memory) of the partitioned
@@ -220,9 +221,10 @@ int sgrace_halo_push(sgrace_handle* h, const void* local, int32_t width, int32_t
 /* the exchange without any SM: copy-engine transfers between peer-visible buffers, ordered on the
  * handle's stream, and 32-bit flag words for the "my rows have landed" signal.
  *   sgrace_peer_copy    dst/src are device addresses on this GPU or peer-mapped ones
- *   sgrace_peer_signal  writes (value mod 65536) to the flag word after all earlier work on the stream
- *   sgrace_wait_flag    makes the stream wait (stream memory operation) until the flag word, in a buffer of
- *                       this GPU, equals (value mod 65536) */
+ *   sgrace_peer_signal  writes the 32-bit epoch `value` to the flag word after all earlier work on the stream
+ *                       (cuStreamWriteValue32)
+ *   sgrace_wait_flag    makes the stream wait (cuStreamWaitValue32, GEQ: wrap-safe) until the flag word, in a
+ *                       buffer of this GPU, has reached `value` */
 int sgrace_peer_copy(sgrace_handle* h, uint64_t dst, uint64_t src, size_t bytes);
 int sgrace_peer_signal(sgrace_handle* h, uint64_t flag_addr, uint32_t value);
 int sgrace_wait_flag(sgrace_handle* h, uint64_t flag_addr, uint32_t value);

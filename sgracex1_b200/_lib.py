@@ -23,7 +23,7 @@ EXPORTS = (
     "sgrace_read_reg", "sgrace_write_reg64", "sgrace_reg_offset", "sgrace_set_option",
     "sgrace_get_option", "sgrace_set_stream", "sgrace_start", "sgrace_done", "sgrace_wait",
     "sgrace_stage_times", "sgrace_layer_run", "sgrace_fea_run", "sgrace_adj_run",
-    "sgrace_launch_count", "sgrace_dense_run", "sgrace_peer_alloc", "sgrace_peer_open", "sgrace_peer_release",
+    "sgrace_launch_count", "sgrace_dense_run", "sgrace_peer_alloc", "sgrace_peer_open", "sgrace_peer_close", "sgrace_peer_release",
     "sgrace_adj_run_peer", "sgrace_halo_gather", "sgrace_halo_push", "sgrace_xty_run",
     "sgrace_peer_copy", "sgrace_peer_signal", "sgrace_wait_flag", "sgrace_sym_norm", "sgrace_dense_to_csr",
 )
@@ -93,6 +93,7 @@ def load():
     lib.sgrace_peer_alloc.argtypes = [H, C.c_size_t, C.POINTER(C.c_uint64), C.c_char_p]
     lib.sgrace_peer_open.argtypes = [H, C.c_char_p, C.POINTER(C.c_uint64)]
     lib.sgrace_peer_release.argtypes = [H]
+    lib.sgrace_peer_close.argtypes = [H]
     lib.sgrace_adj_run_peer.argtypes = [H, C.POINTER(LayerDesc), C.POINTER(C.c_uint64), C.c_int32, C.c_int32]
     lib.sgrace_halo_gather.argtypes = [H, C.POINTER(C.c_uint64), C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     lib.sgrace_halo_push.argtypes = [H, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_int64), C.POINTER(C.c_uint64)]
@@ -231,6 +232,9 @@ class Handle:
         addr = C.c_uint64()
         self._ck(self.lib.sgrace_peer_open(self.h, C.create_string_buffer(bytes(handle_bytes), 64), C.byref(addr)))
         return int(addr.value)
+
+    def peer_close(self):
+        self._ck(self.lib.sgrace_peer_close(self.h))
 
     def peer_release(self):
         self._ck(self.lib.sgrace_peer_release(self.h))

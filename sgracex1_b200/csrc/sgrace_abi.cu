@@ -19,6 +19,7 @@
 #include <string.h>
 
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -60,10 +61,16 @@ struct sgrace_handle {
     std::vector<uint64_t> peer_opened;          // mappings from sgrace_peer_open
     float leaky_alpha = 0.2f;
     // scratch (grow-only)
-    Scratch wrm, wdup, ax, long_partial, long_done, xw, wq, s1, s2, rp_fea, rp_adj, lists, counters;
-    Scratch seq;             // seq[i] = i, the source of sgrace_peer_signal's 4-byte copies
-    Scratch prep_keys, prep_ids, prep_misc, prep_tmp;   // graph preparation (sgrace_sym_norm / sgrace_dense_to_csr)
+    Scratch wrm, ax, long_partial, long_done, xw, wq, s1, s2, rp_fea, rp_adj, lists, counters;
+        Scratch prep_keys, prep_ids, prep_misc, prep_tmp;   // graph preparation (sgrace_sym_norm / sgrace_dense_to_csr)
     int smem_optin = 0;      // cudaDevAttrMaxSharedMemoryPerBlockOptin
+    // streaming-SpMM geometry overrides (0 = built-in default), read from SGRACE_STREAM_* once when the handle is
+    // created; SGRACE_TUNE_LIVE=1 re-reads them at every launch (parameter sweeps from one process)
+    struct StreamTune {
+        int c_s = 0, c_g = 0, g_s = 0, g_g = 0, s_s = 0, s_g = 0, tr_s = 0, tr_g = 0, threads_s = 0, threads_g = 0;
+        int ctas = 0, nosmem = 0, long_noseg = 0, live = 0;
+    } tune;
+    std::map<std::pair<const void*, uint64_t>, int> launch_cfg;   // (kernel, threads << 32 | smem) -> resident CTAs per SM
     int* max_fea_dev = nullptr;
     // state
     bool running = false;
@@ -122,6 +129,45 @@ int env_int(const char* name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
+void load_tune(sgrace_handle* h) {
+    auto& t = h->tune;
+    t.c_s = env_int("SGRACE_STREAM_C", 0); t.c_g = env_int("SGRACE_STREAM_C_G", 0);
+    t.g_s = env_int("SGRACE_STREAM_G_S", 0); t.g_g = env_int("SGRACE_STREAM_G_G", 0);
+    t.s_s = env_int("SGRACE_STREAM_S_S", 0); t.s_g = env_int("SGRACE_STREAM_S_G", 0);
+    t.tr_s = env_int("SGRACE_STREAM_TR", 0); t.tr_g = env_int("SGRACE_STREAM_TR_G", 0);
+    t.threads_s = env_int("SGRACE_STREAM_THREADS_S", 0); t.threads_g = env_int("SGRACE_STREAM_THREADS_G", 0);
+    t.ctas = env_int("SGRACE_STREAM_CTAS", 0);
+    t.nosmem = env_int("SGRACE_STREAM_NOSMEM", 0);
+    t.long_noseg = env_int("SGRACE_LONG_NOSEG", 0);
+    t.live = env_int("SGRACE_TUNE_LIVE", 0);
+}
+
+// resident CTAs per SM of `kern` at this block size / dynamic shared memory; the attribute call and the occupancy
+// query are made once per (kernel, geometry) and handle
+template <typename K>
+int launch_config(sgrace_handle* h, K kern, int threads, size_t smem, int* per_sm) {
+    const auto key = std::make_pair((const void*)kern, ((uint64_t)threads << 32) | (uint64_t)smem);
+    auto it = h->launch_cfg.find(key);
+    if (it != h->launch_cfg.end()) { *per_sm = it->second; return 0; }
+    // the attribute belongs to the kernel (per device, shared by every handle of the process), not to the geometry:
+    // it is only ever raised
+    {
+        static std::mutex mu;
+        static std::map<std::pair<int, const void*>, size_t> granted_by_kernel;
+        std::lock_guard<std::mutex> lock(mu);
+        size_t& granted = granted_by_kernel[std::make_pair(h->device, (const void*)kern)];
+        if (smem > granted) {
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            granted = smem;
+        }
+    }
+    int n = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem));
+    h->launch_cfg[key] = n;
+    *per_sm = n;
+    return 0;
+}
+
 inline int grid_for(long long work_items, int block, int num_sms, int max_waves = 32) {
     long long g = (work_items + block - 1) / block;
     long long cap = (long long)num_sms * max_waves;
@@ -162,7 +208,7 @@ int launch_long_rows(sgrace_handle* h, const int* rp, const int* ci, const float
     const long long max_rows = nnz_hint > 0 ? nnz_hint / (h->long_row > 0 ? h->long_row : 1) + 1 : 0;
     const long long max_segs = nnz_hint > 0 ? nnz_hint / LONG_SEG + max_rows + 1 : 0;
     const size_t part_bytes = (size_t)max_segs * P4 * sizeof(float4);
-    const bool seg = nnz_hint > 0 && part_bytes <= ((size_t)1 << 30) && !env_int("SGRACE_LONG_NOSEG", 0);
+    const bool seg = nnz_hint > 0 && part_bytes <= ((size_t)1 << 30) && !h->tune.long_noseg;
     PeerTable pt;
     memset(&pt, 0, sizeof(pt));
     pt.count = h->peer_count; pt.block = h->peer_block; pt.accumulate = h->accumulate;
@@ -252,79 +298,56 @@ int launch_spmm_stream(sgrace_handle* h, const int* rp, const int* ci, const flo
     const bool exact = (P4 == LPR * NV);
 
     // where Bm rows are gathered from: shared memory when the whole matrix fits beside the stages
+    if (h->tune.live) load_tune(h);
+    const auto& tn = h->tune;
     const size_t budget = (size_t)h->smem_optin;
     const size_t b_plain = (size_t)b_rows * P * 4;
     int bsrc = BSRC_GLOBAL;
     // smem gathers: one CTA per SM split into 4 pipelines of 1 producer + 7 consumer warps with
     // 1024-non-zero stages; global gathers: 2-3 CTAs per SM of one pipeline each, 2048-non-zero stages
     int C = 2048, G = 1, S = 3;
-    if (b_rows > 0 && !env_int("SGRACE_STREAM_NOSMEM", 0)) {
-        if (LPR == 4 && NV == 1 && exact && env_int("SGRACE_STREAM_DUP", 0) &&
-            stream_smem_bytes(4, 2, 64, 512, (int)(2 * b_plain)) <= budget) {
-            bsrc = BSRC_SMEM_DUP;
-            C = 512; G = 4; S = 2;
-        } else if (stream_smem_bytes(4, 2, 128, 1024, (int)b_plain) <= budget) {
-            bsrc = BSRC_SMEM;
-            C = 1024; G = 4; S = 3;
-        }
+    if (b_rows > 0 && !tn.nosmem && stream_smem_bytes(4, 2, 128, 1024, (int)b_plain) <= budget) {
+        bsrc = BSRC_SMEM;
+        C = 1024; G = 4; S = 3;
     }
-    C = env_int("SGRACE_STREAM_C", C) & ~3;
-    if (bsrc == BSRC_GLOBAL) C = env_int("SGRACE_STREAM_C_G", C) & ~3;
-    G = env_int(bsrc == BSRC_GLOBAL ? "SGRACE_STREAM_G_G" : "SGRACE_STREAM_G_S", G);
-    if (G < 1) G = 1;
+    const bool glob = bsrc == BSRC_GLOBAL;
+    if ((glob ? tn.c_g : tn.c_s) > 0) C = (glob ? tn.c_g : tn.c_s) & ~3;
+    if ((glob ? tn.g_g : tn.g_s) > 0) G = glob ? tn.g_g : tn.g_s;
     // stage geometry.  smem gathers: a claimed tile holds ~2.5 stages of non-zeros and is cut into
     // 32 pieces, so a stage is filled to within one piece (~8%) and one claim feeds several stages.
     // global gathers: latency-bound, occupancy matters more than stage fill -> small row-pointer
     // slices (tile ~0.6 stage) so that three CTAs fit an SM.
     const double avg = (nnz_hint > 0 && nrows > 0) ? (double)nnz_hint / nrows : 8.0;
-    int TR = (int)((bsrc == BSRC_GLOBAL ? 0.6 : 2.5) * C / (avg > 1.0 ? avg : 1.0));
+    int TR = (int)((glob ? 0.6 : 2.5) * C / (avg > 1.0 ? avg : 1.0));
     TR = (TR / 32) * 32;
     if (TR < 64) TR = 64;
-    if (TR > (bsrc == BSRC_GLOBAL ? 512 : 1024)) TR = bsrc == BSRC_GLOBAL ? 512 : 1024;
-    TR = env_int("SGRACE_STREAM_TR", TR);
-    if (bsrc == BSRC_GLOBAL) TR = env_int("SGRACE_STREAM_TR_G", TR);
+    if (TR > (glob ? 512 : 1024)) TR = glob ? 512 : 1024;
+    if ((glob ? tn.tr_g : tn.tr_s) > 0) TR = ((glob ? tn.tr_g : tn.tr_s) / 32) * 32;
+    if (TR < 32) TR = 32;
     sp.tile_rows = TR; sp.stage_nnz = C; sp.groups = G;
-
-    sp.b_bytes = bsrc == BSRC_SMEM_DUP ? (int)(2 * b_plain) : bsrc == BSRC_SMEM ? (int)b_plain : 0;
+    sp.b_bytes = glob ? 0 : (int)b_plain;
     sp.Bm = (const float4*)Bm;
-    if (bsrc == BSRC_SMEM_DUP) {
-        if (int rc = ensure(h, h->wdup, 2 * b_plain)) return rc;
-        const int items = b_rows * 8;
-        make_dup_image_kernel<<<(items + 255) / 256, 256, 0, h->stream>>>((const float4*)Bm, (float4*)h->wdup.p, b_rows);
-        h->launches++;
-        CU(cudaGetLastError());
-        sp.Bm = (const float4*)h->wdup.p;
-    }
-    S = env_int(bsrc == BSRC_GLOBAL ? "SGRACE_STREAM_S_G" : "SGRACE_STREAM_S_S", S);
+    if ((glob ? tn.s_g : tn.s_s) > 0) S = glob ? tn.s_g : tn.s_s;
     while (S > 2 && stream_smem_bytes(G, S, TR, C, sp.b_bytes) > budget) S--;
     sp.stages = S;
     const size_t smem = stream_smem_bytes(G, S, TR, C, sp.b_bytes);
     if (smem > budget) return fail(h, SGRACE_EUNSUPPORTED, "streaming SpMM needs %zu bytes of shared memory", smem);
 
-    const int static_pct = env_int("SGRACE_STREAM_STATIC", 0);
-    sp.dry_run = env_int("SGRACE_STREAM_DRY", 0);
-    sp.l1_prefetch = bsrc == BSRC_GLOBAL ? env_int("SGRACE_STREAM_PF", 0) : 0;
-    sp.prefetch_rows = (bsrc == BSRC_GLOBAL && env_int("SGRACE_STREAM_PREFETCH", 0)) ? b_total_rows : 0;
-    sp.prefetch_lead = env_int("SGRACE_STREAM_LEAD", 4096);
-    sp.reverse = (bsrc == BSRC_GLOBAL && final_out) ? env_int("SGRACE_STREAM_REVERSE", 0) : 0;
-#define STREAM_LAUNCH(BS, MT, MB, EX)                                                                          \
+#define STREAM_LAUNCH(BS, MT, MB, EX, PEER)                                                                    \
     do {                                                                                                       \
-        auto kern = spmm_stream_f32_kernel<LPR, NV, BS, MT, MB, EX>;                                           \
-        int threads = env_int(BS == BSRC_GLOBAL ? "SGRACE_STREAM_THREADS_G" : "SGRACE_STREAM_THREADS_S",       \
-                              (BS == BSRC_GLOBAL && MT > 384 && MT < 1024) ? 384 : MT);                        \
+        auto kern = spmm_stream_f32_kernel<LPR, NV, BS, MT, MB, EX, PEER>;                                     \
+        int threads = (BS == BSRC_GLOBAL && MT > 384 && MT < 1024) ? 384 : MT;                                 \
+        if ((BS == BSRC_GLOBAL ? tn.threads_g : tn.threads_s) > 0) threads = BS == BSRC_GLOBAL ? tn.threads_g : tn.threads_s; \
         if (threads > MT) threads = MT;                                                                        \
         threads = (threads / (32 * G)) * (32 * G);                                                             \
         if (threads < 64 * G) threads = 64 * G;                                                                \
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
         int per_sm = 1;                                                                                        \
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));                       \
+        if (int rc = launch_config(h, kern, threads, smem, &per_sm)) return rc;                                \
         if (per_sm < 1) return fail(h, SGRACE_ECUDA, "streaming SpMM does not fit an SM (%zu B smem)", smem);  \
-        const int cap = env_int("SGRACE_STREAM_CTAS", 0);                                                      \
-        if (cap > 0 && per_sm > cap) per_sm = cap;                                                             \
+        if (tn.ctas > 0 && per_sm > tn.ctas) per_sm = tn.ctas;                                                 \
         const long long tiles = ((long long)nrows + TR - 1) / TR;                                              \
         long long grid = (long long)h->num_sms * per_sm;                                                       \
         if (grid > tiles) grid = tiles;                                                                        \
-        sp.static_tiles = (int)(tiles * static_pct / 100 / (grid * G));                                        \
         kern<<<(int)grid, threads, smem, h->stream>>>(sp);                                                     \
     } while (0)
     // register budgets: NV == 1 kernels fit 64 registers -> 1024-thread CTAs (smem gathers) or
@@ -332,36 +355,16 @@ int launch_spmm_stream(sgrace_handle* h, const int* rp, const int* ci, const flo
     // (NV > 1) get 512 x 1 -> 128 registers
     constexpr int MT_SMEM = NV == 1 ? 1024 : 512;
     constexpr int MB_GLOB = NV == 1 ? 2 : 1;
-    if (bsrc == BSRC_SMEM_DUP) {
-        if (LPR == 4 && NV == 1) STREAM_LAUNCH(BSRC_SMEM_DUP, 1024, 1, true);
-    } else if (bsrc == BSRC_SMEM) {
-        if (exact) STREAM_LAUNCH(BSRC_SMEM, MT_SMEM, 1, true); else STREAM_LAUNCH(BSRC_SMEM, 512, 1, false);
+    if (bsrc == BSRC_SMEM) {
+        if (exact) STREAM_LAUNCH(BSRC_SMEM, MT_SMEM, 1, true, false); else STREAM_LAUNCH(BSRC_SMEM, 512, 1, false, false);
     } else if (h->peer_count > 0) {
         // row-partitioned Bm gathered over NVLink; only wide rows (a full warp per row) are instantiated
         sp.peer_count = h->peer_count; sp.peer_block = h->peer_block;
         for (int r = 0; r < MAX_PEERS; r++) sp.peer_base[r] = h->peer_base[r];
         if (LPR != 32) return fail(h, SGRACE_EUNSUPPORTED, "peer gathers need P_w >= 68 (one warp per row)");
-#define STREAM_LAUNCH_PEER(MT, MB, EX)                                                                         \
-        do {                                                                                                   \
-            auto kern = spmm_stream_f32_kernel<LPR, NV, BSRC_GLOBAL, MT, MB, EX, true>;                        \
-            int threads = MT > 384 ? 384 : MT;                                                                 \
-            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
-            int per_sm = 1;                                                                                    \
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));                   \
-            if (per_sm < 1) return fail(h, SGRACE_ECUDA, "streaming SpMM does not fit an SM");                 \
-            const long long tiles = ((long long)nrows + TR - 1) / TR;                                          \
-            long long grid = (long long)h->num_sms * per_sm;                                                   \
-            if (grid > tiles) grid = tiles;                                                                    \
-            sp.static_tiles = 0;                                                                               \
-            kern<<<(int)grid, threads, smem, h->stream>>>(sp);                                                 \
-        } while (0)
-        if (LPR == 32) { if (exact) STREAM_LAUNCH_PEER(512, MB_GLOB, true); else STREAM_LAUNCH_PEER(512, 1, false); }
-#undef STREAM_LAUNCH_PEER
-    } else if (exact && NV == 1 && env_int("SGRACE_STREAM_BIGG", 0)) {
-        // experiment: one 1024-thread CTA per SM walking a contiguous row range, L1 left to the gathered rows
-        if (NV == 1) STREAM_LAUNCH(BSRC_GLOBAL, 1024, 1, true);
+        if (LPR == 32) { if (exact) STREAM_LAUNCH(BSRC_GLOBAL, 512, MB_GLOB, true, true); else STREAM_LAUNCH(BSRC_GLOBAL, 512, 1, false, true); }
     } else {
-        if (exact) STREAM_LAUNCH(BSRC_GLOBAL, 512, MB_GLOB, true); else STREAM_LAUNCH(BSRC_GLOBAL, 512, 1, false);
+        if (exact) STREAM_LAUNCH(BSRC_GLOBAL, 512, MB_GLOB, true, false); else STREAM_LAUNCH(BSRC_GLOBAL, 512, 1, false, false);
     }
 #undef STREAM_LAUNCH
     h->launches++;
@@ -968,6 +971,7 @@ int sgrace_create(int device, sgrace_handle** out) {
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     for (int i = 0; i < 5; i++) cudaEventCreate(&h->ev[i]);
+    load_tune(h);
     *out = h;
     return SGRACE_OK;
 }
@@ -980,7 +984,7 @@ int sgrace_destroy(sgrace_handle* h) {
         cudaFree(kv.second.dev);
         cudaFreeHost(kv.second.host);
     }
-    Scratch* all[] = {&h->wrm, &h->wdup, &h->ax, &h->long_partial, &h->long_done, &h->xw, &h->wq, &h->s1, &h->s2, &h->rp_fea, &h->rp_adj, &h->lists, &h->counters, &h->seq, &h->prep_keys, &h->prep_ids, &h->prep_misc, &h->prep_tmp};
+    Scratch* all[] = {&h->wrm, &h->ax, &h->long_partial, &h->long_done, &h->xw, &h->wq, &h->s1, &h->s2, &h->rp_fea, &h->rp_adj, &h->lists, &h->counters, &h->prep_keys, &h->prep_ids, &h->prep_misc, &h->prep_tmp};
     for (Scratch* s : all) if (s->p) cudaFree(s->p);
     if (h->max_fea_dev) cudaFree(h->max_fea_dev);
     for (int i = 0; i < 5; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -1210,12 +1214,21 @@ int sgrace_peer_open(sgrace_handle* h, const unsigned char handle_in[64], uint64
     return SGRACE_OK;
 }
 
-int sgrace_peer_release(sgrace_handle* h) {
+// Teardown in two steps with a barrier between them on the caller's side: every rank first closes the mappings it
+// imported (sgrace_peer_close), then -- once all ranks have done so -- frees what it exported (sgrace_peer_release).
+// Freeing exported memory that a peer still has mapped is undefined behaviour.
+int sgrace_peer_close(sgrace_handle* h) {
     if (!h) return SGRACE_EINVAL;
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
     for (uint64_t a : h->peer_opened) cudaIpcCloseMemHandle((void*)(uintptr_t)a);
     h->peer_opened.clear();
+    return SGRACE_OK;
+}
+
+int sgrace_peer_release(sgrace_handle* h) {
+    if (!h) return SGRACE_EINVAL;
+    if (int rc = sgrace_peer_close(h)) return rc;
     for (auto& kv : h->peer_allocs) cudaFree((void*)(uintptr_t)kv.first);
     h->peer_allocs.clear();
     return SGRACE_OK;
@@ -1231,18 +1244,31 @@ int sgrace_peer_copy(sgrace_handle* h, uint64_t dst, uint64_t src, size_t bytes)
     return SGRACE_OK;
 }
 
+// Flag protocol of the copy-engine exchange: a sender bumps a 32-bit epoch word in the receiver's peer-visible
+// memory with a stream memory operation ordered after its copies; the receiver's stream waits until the word has
+// reached the epoch (CU_STREAM_WAIT_VALUE_GEQ compares (int32)(*addr - value) >= 0, so it is wrap-safe and a sender
+// that has already posted a later epoch never strands a wait).
+extern "C++" {
+template <typename Fn>
+static Fn driver_entry(const char* name) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+        return reinterpret_cast<Fn>(p);
+    return nullptr;
+}
+}
+
 int sgrace_peer_signal(sgrace_handle* h, uint64_t flag_addr, uint32_t value) {
     if (!h) return SGRACE_EINVAL;
     h->last_status = 0;
     CU(cudaSetDevice(h->device));
     if (!flag_addr || (flag_addr & 3)) return fail(h, SGRACE_EINVAL, "peer signal: bad flag address");
-    if (!h->seq.p) {
-        if (int rc = ensure(h, h->seq, sizeof(uint32_t) * 65536)) return rc;
-        iota_u32_kernel<<<64, 1024, 0, h->stream>>>((uint32_t*)h->seq.p, 65536);
-        CU(cudaGetLastError());
-        h->launches++;
-    }
-    CU(cudaMemcpyAsync((void*)(uintptr_t)flag_addr, (const uint32_t*)h->seq.p + (value & 0xffffu), 4, cudaMemcpyDeviceToDevice, h->stream));
+    typedef CUresult (*WriteValueFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+    static WriteValueFn fn = driver_entry<WriteValueFn>("cuStreamWriteValue32");
+    if (!fn) return fail(h, SGRACE_EUNSUPPORTED, "cuStreamWriteValue32 is not available in this driver");
+    const CUresult r = fn((CUstream)h->stream, (CUdeviceptr)flag_addr, (cuuint32_t)value, CU_STREAM_WRITE_VALUE_DEFAULT);
+    if (r != CUDA_SUCCESS) return fail(h, SGRACE_ECUDA, "cuStreamWriteValue32 failed (%d)", (int)r);
     return SGRACE_OK;
 }
 
@@ -1252,15 +1278,9 @@ int sgrace_wait_flag(sgrace_handle* h, uint64_t flag_addr, uint32_t value) {
     CU(cudaSetDevice(h->device));
     if (!flag_addr || (flag_addr & 3)) return fail(h, SGRACE_EINVAL, "wait flag: bad flag address");
     typedef CUresult (*WaitValueFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
-    static WaitValueFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<WaitValueFn>(p);
-    }
+    static WaitValueFn fn = driver_entry<WaitValueFn>("cuStreamWaitValue32");
     if (!fn) return fail(h, SGRACE_EUNSUPPORTED, "cuStreamWaitValue32 is not available in this driver");
-    const CUresult r = fn((CUstream)h->stream, (CUdeviceptr)flag_addr, (cuuint32_t)(value & 0xffffu), CU_STREAM_WAIT_VALUE_EQ);
+    const CUresult r = fn((CUstream)h->stream, (CUdeviceptr)flag_addr, (cuuint32_t)value, CU_STREAM_WAIT_VALUE_GEQ);
     if (r != CUDA_SUCCESS) return fail(h, SGRACE_ECUDA, "cuStreamWaitValue32 failed (%d)", (int)r);
     return SGRACE_OK;
 }

@@ -392,11 +392,6 @@ dense_adj_f32_kernel(const float* __restrict__ A, const float4* __restrict__ Bm,
     }
 }
 
-__global__ void iota_u32_kernel(uint32_t* out, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (uint32_t)i;
-}
-
 // Long rows: one CTA per listed row.  Each warp walks a contiguous slice of the row's
 // non-zeros; lanes own float4 column chunks (q = lane, lane+32, ...), warps' partials
 // are combined in warp order through shared memory -> deterministic.

@@ -24,9 +24,10 @@
 //     mbarrier and the producer refills it.
 //   * Bm is either gathered from global memory through L1 (ADJ: Bm = XW; FEA with a weight
 //     matrix too large for shared memory) or staged once per CTA in shared memory (FEA: the
-//     Cora-shape W is 1433 x 16 floats = 92 KB).  With 64-byte rows two row groups share one
-//     shared-memory wavefront; the DUP layout keeps two copies of every row, one per half of
-//     the banks, so that the two groups never collide.
+//     Cora-shape W is 1433 x 16 floats = 92 KB).  With 64-byte rows two row groups of a quarter-warp
+//     share one shared-memory wavefront when their rows have opposite parity and take two otherwise
+//     (a duplicated image that removes the conflict leaves too little room for stages: measured
+//     0.32 ms against 0.25 ms).
 //   * rows longer than `long_thresh` (or than a stage) are appended to a list and handled by
 //     spmm_long_rows_f32_kernel afterwards (row-bucket scheduling for power-law graphs).
 // Accumulation is float FMA in CSR order within a row: deterministic, no atomics on values.
@@ -36,7 +37,7 @@
 
 namespace sgrace {
 
-enum { BSRC_GLOBAL = 0, BSRC_SMEM = 1, BSRC_SMEM_DUP = 2 };
+enum { BSRC_GLOBAL = 0, BSRC_SMEM = 1 };
 constexpr int MAX_PEERS = 8;
 
 struct StreamParams {
@@ -54,14 +55,6 @@ struct StreamParams {
     int b_bytes;             // bytes of the Bm image staged in shared memory (SMEM*), multiple of 16
     int streaming_store;     // 1: out is not re-read soon (D) -> st.global.cs
     int accumulate;          // 1: out = act(out + A.Bm)  (second pass over a split adjacency)
-    int static_tiles;        // tiles each CTA owns as one contiguous run before it claims dynamically
-    int l1_prefetch;         // GLOBAL gathers: passes of next-row Bm prefetch per group (0 = off)
-    int dry_run;             // debug: stream the stages but skip the arithmetic (feed-rate measurement)
-    int prefetch_rows;       // > 0 (GLOBAL): rows of Bm; the producer L2-prefetches the Bm rows `prefetch_lead` rows
-                             //     ahead of each sub-tile (near-diagonal adjacencies: batched graphs, banded orderings)
-    int prefetch_lead;
-    int reverse;             // 1: tiles are walked from the last row to the first (ADJ right after FEA: the rows of XW
-                             //     written last are still in L2)
     int* long_rows;
     int* long_count;
     int* tile_counter;
@@ -113,11 +106,6 @@ struct StageHeader {
     int kbase;       // global index of the non-zero stored at col_s[0] / val_s[0] (multiple of 4)
     int roff;        // rp_s[roff + i] is rowptr[row_begin + i]
 };
-
-// L2 prefetch of a contiguous global range (no shared-memory destination, no completion tracking)
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
 
 __device__ __forceinline__ void fma4s(float4& a, float s, const float4& b) {
     a.x = fmaf(s, b.x, a.x); a.y = fmaf(s, b.y, a.y);
@@ -242,15 +230,6 @@ spmm_stream_f32_kernel(const StreamParams p) {
                 StageHeader h;
                 h.row_begin = rb; h.nrows = re - rb; h.kbase = kb_al; h.roff = rb - rb_al;
                 hdr[stage] = h;
-                if (BSRC == BSRC_GLOBAL && p.prefetch_rows > 0) {
-                    // the band of Bm rows the walk will reach `prefetch_lead` rows from now: every row of the
-                    // band is requested once, long before the gathers that need it
-                    const int shift = p.reverse ? -p.prefetch_lead : p.prefetch_lead;
-                    const int pb = max(rb + shift, 0), pe = min(re + shift, p.prefetch_rows);
-                    if (pe > pb)
-                        bulk_prefetch_l2(reinterpret_cast<const char*>(p.Bm) + (size_t)pb * p.P4 * 16,
-                                         (uint32_t)(pe - pb) * (uint32_t)p.P4 * 16u);
-                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive_expect_tx(full + stage, tx);
@@ -259,22 +238,14 @@ spmm_stream_f32_kernel(const StreamParams p) {
 
         // Tiles are claimed two ahead and their row-pointer samples loaded one ahead, so the atomic
         // and the sample loads of the coming tiles are in flight while this tile is being streamed.
-        // A CTA first walks its own contiguous run of `static_tiles` tiles (neighbouring rows gather
-        // neighbouring Bm rows, which keeps them in this SM's L1), then claims the remaining tiles
-        // one at a time from the global counter (load balance).
-        int seq = 0;
-        const int static_total = p.static_tiles * (int)gridDim.x * G;
+        // Tiles come from a global counter (load balance; a static split was measured slower).
         auto claim = [&]() -> int {
-            int t = 0;
-            if (seq < p.static_tiles) t = (int)blockIdx.x * (G * p.static_tiles) + seq * G + grp;   // groups of a CTA interleave
-            else if (lane == 0) t = static_total + atomicAdd(p.tile_counter, 1);
-            seq++;
-            return t;                               // valid in lane 0 only until shuffled
+            return lane == 0 ? atomicAdd(p.tile_counter, 1) : 0;    // valid in lane 0 only until shuffled
         };
         const int ntiles = (p.nrows + TR - 1) / TR;
         // piece j of a tile covers rows [a + j*SUB, a + (j+1)*SUB) clipped to the tile
         auto sample = [&](int t, int& r_lo, int& r_hi, int& s_lo, int& s_hi) {
-            const long long a_ll = t < ntiles ? (long long)(p.reverse ? ntiles - 1 - t : t) * TR : (long long)p.nrows;
+            const long long a_ll = t < ntiles ? (long long)t * TR : (long long)p.nrows;
             const int a = a_ll < p.nrows ? (int)a_ll : p.nrows;
             const int tile_end = min(a + TR, p.nrows);
             r_lo = min(a + lane * SUB, tile_end);
@@ -288,7 +259,7 @@ spmm_stream_f32_kernel(const StreamParams p) {
         int t_next_raw = claim();
         for (;;) {
             if (t_cur >= ntiles) break;
-            const int a = (p.reverse ? ntiles - 1 - t_cur : t_cur) * TR;
+            const int a = t_cur * TR;
             const int tile_end = min(a + TR, p.nrows);
             const int r_lo = n_rlo, r_hi = n_rhi, s_lo = n_slo, s_hi = n_shi;
             // next tile: its claim was issued an iteration ago; issue its samples and the claim after it
@@ -354,12 +325,9 @@ spmm_stream_f32_kernel(const StreamParams p) {
     uint32_t bs_rowbytes = 0;
     if (BSRC == BSRC_GLOBAL) {
         bg_lane = reinterpret_cast<const char*>(p.Bm + l);
-    } else if (BSRC == BSRC_SMEM) {
+    } else {
         bs_lane = Bs + l * 16;
         bs_rowbytes = rowbytes;
-    } else {   // DUP: row stride 2 x 64 B, odd groups read the second copy (other half of the banks)
-        bs_lane = Bs + (g & 1) * 64 + l * 16;
-        bs_rowbytes = 128;
     }
     if (BSRC != BSRC_GLOBAL) mbar_wait(bfull, 0);
 
@@ -395,24 +363,8 @@ spmm_stream_f32_kernel(const StreamParams p) {
         const int* col_k = reinterpret_cast<const int*>(st + rp_bytes) - h.kbase;
         const float* val_k = reinterpret_cast<const float*>(st + rp_bytes + arr_bytes) - h.kbase;
 
-        for (int i = cw * RPW + g; i < h.nrows && !p.dry_run; i += ncw * RPW) {
+        for (int i = cw * RPW + g; i < h.nrows; i += ncw * RPW) {
             const int beg = rp_s[i], end = rp_s[i + 1];
-            if (BSRC == BSRC_GLOBAL && p.l1_prefetch) {
-                // Software pipelining without registers: pull the Bm rows of the group's NEXT row towards
-                // this SM while the current row is processed (a group of LPR lanes covers LPR non-zeros
-                // per pass, `l1_prefetch` passes; each lane touches its own 16-byte chunk of the row).
-                const int inext = i + ncw * RPW;
-                if (inext < h.nrows) {
-                    const int nb = rp_s[inext], ne = rp_s[inext + 1];
-                    for (int pass = 0, k = nb + l; pass < p.l1_prefetch && k < ne; pass++, k += LPR) {
-                        const int c = col_k[k];
-#pragma unroll
-                        for (int v = 0; v < NV; v++)
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(bg_lane - (size_t)l * 16 + (size_t)(unsigned)c * rowbytes +
-                                                                             (size_t)((v * LPR + (l & (LPR - 1))) * 16)));
-                    }
-                }
-            }
             float4 acc[NV];
 #pragma unroll
             for (int v = 0; v < NV; v++) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -473,15 +425,6 @@ spmm_stream_f32_kernel(const StreamParams p) {
         if (lane == 0) mbar_arrive(empty + stage);
         if (++stage == S) { stage = 0; fphase ^= 1; }
     }
-}
-
-// W (row-major M x P floats) -> the duplicated shared-memory image: row stride 128 B holding the
-// 64-byte row twice
-__global__ void make_dup_image_kernel(const float4* __restrict__ Wrm, float4* __restrict__ img, int M) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // one float4 of the image
-    if (i >= M * 8) return;
-    const int m = i >> 3, q = i & 3;
-    img[i] = Wrm[m * 4 + q];
 }
 
 }  // namespace sgrace

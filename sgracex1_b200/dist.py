@@ -95,6 +95,39 @@ class RowPartitionedLayer:
             dist.all_gather_into_tensor(self.xw_full, slot, group=self.group)
         return self.adj_fn(adj_local, self.xw_full, relu)
 
+    def forward_pipelined(self, x_local, W, adj_local, relu, col_blocks=4):
+        """The same layer with the exchange chunked over column blocks of XW: block c is all-gathered on
+        a side stream while the feature stage computes block c+1, and the aggregation of block c runs under the
+        gather of block c+1.  Every block is an independent (N x P/col_blocks) layer, so each output element is
+        computed exactly as in forward(): the result is bit-identical.  Returns D_local (n x P)."""
+        P = W.shape[1]
+        if self.world == 1 or col_blocks <= 1 or P % col_blocks or (P // col_blocks) % 4:
+            return self.forward(x_local, W, adj_local, relu)
+        Pc = P // col_blocks
+        n = self.hi - self.lo
+        dev = x_local.device
+        if getattr(self, "_blk", None) is None or self._blk[0].shape[1] != Pc or len(self._blk) != col_blocks:
+            self._blk = [torch.zeros(self.block * self.world, Pc, dtype=torch.float32, device=dev) for _ in range(col_blocks)]
+            self._comm = torch.cuda.Stream(dev)
+            self._ev_f = [torch.cuda.Event() for _ in range(col_blocks)]
+            self._ev_g = [torch.cuda.Event() for _ in range(col_blocks)]
+        main = torch.cuda.current_stream(dev)
+        keep = []
+        for c in range(col_blocks):
+            slot = self._blk[c][self.rank * self.block:(self.rank + 1) * self.block]
+            keep.append(self.fea_fn(x_local, W[:, c * Pc:(c + 1) * Pc], slot[:n]))
+            self._ev_f[c].record(main)
+            self._comm.wait_event(self._ev_f[c])
+            with torch.cuda.stream(self._comm):
+                dist.all_gather_into_tensor(self._blk[c], slot, group=self.group)
+            self._ev_g[c].record(self._comm)
+        outs = []
+        for c in range(col_blocks):
+            main.wait_event(self._ev_g[c])
+            outs.append(self.adj_fn(adj_local, self._blk[c], relu))
+        self._comm.wait_stream(main)          # the next layer's gathers must not overwrite blocks still being read
+        return torch.cat(outs, dim=1)
+
 
 def abi_fea_fn(handle):
     from . import _lib
@@ -190,8 +223,8 @@ class PeerGatherLayer:
         self.h.dense_run(t.data_ptr(), Bt.data_ptr(), out.data_ptr(), t.shape[0], M, P, relu)
         return out, (t, Bt)
 
-    def release(self):
-        self.h.peer_release()
+    def release(self, barrier=None):
+        _teardown(self.h, [], [], barrier)
 
 
 # ------------------------------------------------------------------------------------------
@@ -280,6 +313,7 @@ class HaloLayer:
         if exchange != "defer" and world > 1:
             self._exchange_push_lists(halo_rows, device)
         self.s_main = torch.cuda.current_stream(device)
+        self.hm.set_stream(self.s_main.cuda_stream)      # ev_ready / ev_halo order kernels only if hm launches here
         self.s_halo = torch.cuda.Stream(device)
         self.hh.set_stream(self.s_halo.cuda_stream)
         self.ev_ready, self.ev_halo = torch.cuda.Event(), torch.cuda.Event()
@@ -460,8 +494,23 @@ class HaloLayer:
                           halo_rows=self.n_halo, halo_mb=self.n_halo * self.width * 4 / 1e6, nnz_remote=self.nnz_remote)
         return out, (t, Bt)
 
-    def release(self):
-        self.hm.peer_release()
+    def release(self, barrier=None):
+        """Close the imported mappings on every rank, barrier, then free the exported buffers (freeing memory a
+        peer still has mapped is undefined behaviour).  `barrier`: callable; torch.distributed's when omitted."""
+        _teardown(self.hm, [sx for _, sx, _ in self.copy_lanes], [hx for hx, _, _ in self.copy_lanes[1:]], barrier)
+
+
+def _teardown(hm, streams, extra_handles, barrier):
+    for sx in streams:
+        sx.synchronize()
+    hm.peer_close()
+    if barrier is not None:
+        barrier()
+    elif dist.is_available() and dist.is_initialized():
+        dist.barrier()
+    hm.peer_release()
+    for hx in extra_handles:
+        hx.close()
 
 
 # ------------------------------------------------------------------------------------------
@@ -578,6 +627,7 @@ class ChunkedHaloLayer:
         if exchange != "defer":
             self.set_push_lists((gather or exchange)(self.wants), device)
         self.s_main = torch.cuda.current_stream(device)
+        self.hm.set_stream(self.s_main.cuda_stream)
         self.lanes = []
         for _ in range(2):                       # send, wait
             hx, sx = _lib.Handle(device.index or 0), torch.cuda.Stream(device)
@@ -663,13 +713,16 @@ class ChunkedHaloLayer:
             self.s_main.wait_event(self.ev_chunk[c])
             self._adj(self.a_rem[c], t.data_ptr() + r0 * self.width * 4, True)
             self.hm.dense_run(t.data_ptr() + r0 * self.width * 4, Bt.data_ptr(), out.data_ptr() + r0 * P * 4, r1 - r0, M, P, relu)
+        # every flag wait of this layer is ordered before whatever the caller puts on the main stream next (the
+        # token all-reduce of the next layer), also on a rank whose chunks are all empty
+        self.s_main.wait_event(self.ev_chunk[self.n_chunks - 1])
         return out, (t, Bt)
 
     def forward(self, W, relu, timing=None):
         return self.forward_end(self.forward_begin(), W, relu)
 
-    def release(self):
-        self.hm.peer_release()
+    def release(self, barrier=None):
+        _teardown(self.hm, [sx for _, sx in self.lanes], [hx for hx, _ in self.lanes], barrier)
 
 
 # ------------------------------------------------------------------------------------------
@@ -833,3 +886,182 @@ def bench_products(args):
         if order == "agg_first":
             layer.release()
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------
+# strong-scaling record of the default bench.py run at N > 1 (BASELINE configs[4])
+# ------------------------------------------------------------------------------------------
+def products_strong_record(steps, warmup, rank, world, local, scale=1.0, sample_rows=64, halo_chunks=1):
+    """ogbn-products-shape dense layer on `world` GPUs AND on one GPU in the same run, both orders:
+
+      agg_first  act((A.X).W): halo exchange of the referenced rows of X (HaloLayer / ChunkedHaloLayer)
+      reference  act(A.(X.W)): all-gather of XW, one blocking NCCL call and the column-block pipeline
+
+    The process group must exist.  Rank 0 then rebuilds the whole graph from the same per-rank generators, runs
+    the layer alone and compares `sample_rows` rows of every rank's result with its own (matches_single_gpu).
+    Returns the record on rank 0, None elsewhere."""
+    from . import _lib
+    from . import graphs as G
+
+    dev = torch.device(f"cuda:{local}")
+    N = int(2_449_029 * scale)
+    M, P = 100, 256
+    lo, hi = row_range(N, rank, world)
+    n = hi - lo
+    t0 = time.time()
+    rp, ci, va = G.products_shape_rows(lo, hi, n_total=N)
+    gen_s = time.time() - t0
+    x_np = np.random.default_rng([2, rank]).standard_normal((n, M), dtype=np.float32)
+    x_local = torch.from_numpy(x_np).to(dev)
+    W = torch.from_numpy(np.random.default_rng(2).uniform(-0.1, 0.1, size=(M, P)).astype(np.float32)).to(dev)
+    adj_local = tuple(torch.from_numpy(a).to(dev) for a in (rp, ci, va))
+    stream = torch.cuda.current_stream(dev)
+    handle = _lib.Handle(local)
+    handle.set_option(_lib.OPT_MODE, _lib.MODE_F32_FAST)
+    handle.set_option(_lib.OPT_STAGING, 0)
+    handle.set_stream(stream.cuda_stream)
+    token = torch.zeros(1, device=dev)
+    pick = torch.from_numpy(np.linspace(0, n - 1, sample_rows).astype(np.int64)).to(dev)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step):
+        out = None
+        for _ in range(max(warmup, 3)):
+            out = step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = step()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), out
+
+    res, samples = {}, {}
+    # ---- aggregate-first order: halo exchange ----
+    handle2 = _lib.Handle(local)
+    handle2.set_option(_lib.OPT_MODE, _lib.MODE_F32_FAST)
+    handle2.set_option(_lib.OPT_STAGING, 0)
+    if halo_chunks > 1:
+        layer = ChunkedHaloLayer(handle, (rp, ci, va), N, M, rank, world, dev, halo_chunks)
+    else:
+        layer = HaloLayer(handle, handle2, (rp, ci, va), N, M, rank, world, dev)
+    layer.local[:n].copy_(x_local)
+    barrier()
+
+    def step_halo():
+        dist.all_reduce(token)              # every rank's X is in place before anyone reads it
+        return layer.forward(W, 1)[0]
+    ms, out = timed(step_halo)
+    exch_ms = None
+    if halo_chunks <= 1:
+        tm = {}
+        dist.all_reduce(token)
+        layer.forward(W, 1, timing=tm)
+        barrier()
+        exch = torch.tensor([tm.get("halo_gather_ms", 0.0)], dtype=torch.float64, device=dev)
+        dist.all_reduce(exch, op=dist.ReduceOp.MAX)
+        exch_ms = float(exch.item())
+    halo_bytes = int(layer.n_halo * M * 4)
+    hb = torch.tensor([float(halo_bytes)], dtype=torch.float64, device=dev)
+    dist.all_reduce(hb, op=dist.ReduceOp.MAX)
+    res["agg_first"] = {"ms_n": ms, "exchange": "halo rows of X over NVLink (copy engines + stream flag waits), overlapped with the "
+                        "aggregation of the owned columns" + (f", pipelined over {halo_chunks} row chunks" if halo_chunks > 1 else ""),
+                        "exchanged_bytes_per_gpu": int(hb.item()), "exchange_ms": exch_ms,
+                        "exchange_gbs_per_gpu": (hb.item() / (exch_ms * 1e-3) / 1e9) if exch_ms else None}
+    samples["agg_first"] = out[pick].clone()
+    del out
+    barrier()
+    layer.release()
+    # ---- reference order: all-gather of XW ----
+    rpl = RowPartitionedLayer(N, P, rank, world, dev, abi_fea_fn(handle), abi_adj_fn(handle))
+    ag_bytes = int(rpl.block * (world - 1) * P * 4)
+    ms_block, out = timed(lambda: rpl.forward(x_local, W, adj_local, 1))
+    samples["reference"] = out[pick].clone()
+    del out
+    ms_pipe, out = timed(lambda: rpl.forward_pipelined(x_local, W, adj_local, 1, col_blocks=4))
+    same_pipe = bool(torch.equal(out[pick], samples["reference"]))
+    del out
+    # the all-gather alone
+    slot = rpl.xw_full[rank * rpl.block:(rank + 1) * rpl.block]
+    ms_ag, _ = timed(lambda: dist.all_gather_into_tensor(rpl.xw_full, slot))
+    res["reference"] = {"ms_n": min(ms_block, ms_pipe), "ms_n_blocking_all_gather": ms_block, "ms_n_pipelined_4_column_blocks": ms_pipe,
+                        "pipelined_equals_blocking": same_pipe, "exchange": "NCCL all-gather of XW",
+                        "exchanged_bytes_per_gpu": ag_bytes, "exchange_ms": ms_ag,
+                        "exchange_gbs_per_gpu": ag_bytes / (ms_ag * 1e-3) / 1e9}
+    del rpl
+    torch.cuda.empty_cache()
+    # ---- every rank's sample to rank 0 ----
+    got = {}
+    for k in ("agg_first", "reference"):
+        buf = [torch.empty_like(samples[k]) for _ in range(world)] if rank == 0 else None
+        dist.gather(samples[k], buf, dst=0)
+        got[k] = buf
+    if rank != 0:
+        barrier()                            # rank 0 runs the one-GPU layer meanwhile
+        return None
+    # ---- one GPU, same run: the whole graph from the same generators ----
+    t0 = time.time()
+    parts = [(rp, ci, va)] + [G.products_shape_rows(*row_range(N, r, world), n_total=N) for r in range(1, world)]
+    rp_full = np.concatenate([[0]] + [p_[0][1:].astype(np.int64) + off for p_, off in
+                                      zip(parts, np.concatenate([[0], np.cumsum([int(p_[0][-1]) for p_ in parts])[:-1]]))]).astype(np.int32)
+    ci_full = np.concatenate([p_[1] for p_ in parts])
+    va_full = np.concatenate([p_[2] for p_ in parts])
+    x_full = torch.cat([x_local] + [torch.from_numpy(np.random.default_rng([2, r]).standard_normal(
+        (row_range(N, r, world)[1] - row_range(N, r, world)[0], M), dtype=np.float32)).to(dev) for r in range(1, world)])
+    adj_full = tuple(torch.from_numpy(a).to(dev) for a in (rp_full, ci_full, va_full))
+    gen1_s = time.time() - t0
+    del parts
+
+    def timed1(step):
+        out = None
+        for _ in range(max(warmup, 3)):
+            out = step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = step()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, out
+
+    one = RowPartitionedLayer(N, P, 0, 1, dev, abi_fea_fn(handle), abi_adj_fn(handle))
+    ms1_ref, d_ref = timed1(lambda: one.forward(x_full, W, adj_full, 1))
+    handle.set_option(_lib.OPT_AGG_FIRST, 1)
+    Bt = W.t().contiguous()
+    d_agg = torch.empty(N, P, device=dev)
+    d = _lib.LayerDesc()
+    d.gemm_mode, d.relu, d.N_adj, d.M_adj, d.M_fea, d.P_w = 1, 1, N, N, M, P
+    d.values_fea, d.B, d.D = x_full.data_ptr(), Bt.data_ptr(), d_agg.data_ptr()
+    d.rowPtr_adj, d.columnIndex_adj, d.values_adj = adj_full[0].data_ptr(), adj_full[1].data_ptr(), adj_full[2].data_ptr()
+    d.nnz_adj = int(adj_full[1].numel())
+
+    def step_agg1():
+        handle.layer_run(d)
+        return d_agg
+    ms1_agg, _ = timed1(step_agg1)
+    handle.set_option(_lib.OPT_AGG_FIRST, 0)
+    for k, ms1, full in (("agg_first", ms1_agg, d_agg), ("reference", ms1_ref, d_ref)):
+        worst = 0.0
+        for r in range(world):
+            lo_r, hi_r = row_range(N, r, world)
+            rows = torch.from_numpy(np.linspace(0, hi_r - lo_r - 1, sample_rows).astype(np.int64)).to(dev) + lo_r
+            want = full[rows]
+            scale_ = want.abs().amax(dim=1, keepdim=True).clamp_min(1e-30)
+            worst = max(worst, float(((got[k][r] - want).abs() / scale_).max().item()))
+        res[k].update(ms_1=ms1, speedup=ms1 / res[k]["ms_n"], matches_single_gpu=bool(worst <= 1e-5), max_rel_err_vs_single_gpu=worst)
+    nnz_total = int(rp_full[-1])
+    best = max(res, key=lambda k: res[k]["speedup"])
+    rec = {"workload": "products", "scaling": "strong", "n_gpus": world, "nodes": N, "nnz_adj": nnz_total, "features": M, "hidden": P,
+           "steps": steps, "orders": res, "best_order": best, "speedup_1_to_n": res[best]["speedup"],
+           "gteps_n": nnz_total / (res[best]["ms_n"] * 1e-3) / 1e9, "graph_gen_s": {"per_rank": gen_s, "whole_graph_on_rank0": gen1_s},
+           "note": "ms_1 and ms_n measured in this run; sample of %d rows per rank compared with the one-GPU result "
+                   "(row-normalised, bar 1e-5)" % sample_rows}
+    barrier()
+    return rec

@@ -421,8 +421,9 @@ def evaluate(model, loader, buffers):
 # ------------------------------------------------------------------------------------------
 # bench.py --workload molecule : data-parallel training, graphs/s
 # ------------------------------------------------------------------------------------------
-def bench_molecule(args):
-    import json
+def molecule_record(steps, warmup, rank, world, local, graphs_per_rank=188 * 64, hidden=64):
+    """Molecule-GCN training (two accelerator layers forward, saved-tensor backward, DP gradient all-reduce, Adam),
+    graphs sharded over the ranks.  The process group must exist when world > 1.  Returns the record on rank 0."""
     import os
 
     import torch.distributed as dist
@@ -430,15 +431,7 @@ def bench_molecule(args):
     from . import dist as sdist
     from . import graphs as G
 
-    rank, world, local = sdist.dist_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    graphs_per_rank = int(getattr(args, "graphs", 0) or 188 * 64)
-    hidden = int(getattr(args, "hidden", 0) or 64)
     prob, batch_np, y_np = G.molecule_batch(n_graphs=graphs_per_rank, seed=12345 + rank, P=hidden)
     handle = _lib.Handle(local)
     handle.set_option(_lib.OPT_STAGING, 0)
@@ -469,18 +462,16 @@ def bench_molecule(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # the whole training step (two accelerator layers forward, saved-tensor backward, gradient all-reduce,
-    # Adam) is launch-bound at this size: capture it once in a CUDA graph and replay it
+    # the whole training step is launch-bound at this size: capture it once in a CUDA graph and replay it
     side = torch.cuda.Stream()
     model.train()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
         l0 = handle.launch_count()
-        for _ in range(max(args.warmup, 3)):
+        for _ in range(max(warmup, 3)):
             step()
-        launches_per_step = (handle.launch_count() - l0) // max(args.warmup, 3)
+        launches_per_step = (handle.launch_count() - l0) // max(warmup, 3)
     barrier()
-    graph = None
     if use_graph:
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
@@ -495,27 +486,46 @@ def bench_molecule(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(args.steps):
+        for _ in range(steps):
             run()
         e1.record()
     barrier()
-    ms = e0.elapsed_time(e1) / args.steps
-    launches = launches_per_step * args.steps
-    loss = loss_buf
+    ms = e0.elapsed_time(e1) / steps
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    torch.cuda.current_stream().wait_stream(side)
+    if rank != 0:
+        return None
+    return {
+        "metric": "molecule_gcn_graphs_per_s", "value": total_graphs / (ms * 1e-3), "unit": "graphs/s",
+        "n_gpus": world, "steps": steps, "warmup": max(warmup, 3), "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "molecule", "graphs_per_step_per_gpu": graphs_per_rank, "nodes_per_gpu": prob.N,
+                   "nnz_adj_per_gpu": prob.nnz_adj, "hidden": hidden,
+                   "mode": "2-layer GCN forward on the accelerator + saved-tensor backward, Adam, DP grad all-reduce",
+                   "cuda_graph": bool(use_graph)},
+        "gpu_launches": int(launches_per_step * steps), "loss": float(loss_buf.item()),
+    }
+
+
+def bench_molecule(args):
+    import json
+
+    import torch.distributed as dist
+
+    from . import dist as sdist
+
+    rank, world, local = sdist.dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    rec = molecule_record(args.steps, args.warmup, rank, world, local, int(getattr(args, "graphs", 0) or 188 * 64),
+                          int(getattr(args, "hidden", 0) or 64))
     if rank == 0:
-        print(json.dumps({
-            "metric": "molecule_gcn_graphs_per_s", "value": total_graphs / (ms * 1e-3), "unit": "graphs/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "molecule", "graphs_per_step_per_gpu": graphs_per_rank, "nodes_per_gpu": prob.N,
-                       "nnz_adj_per_gpu": prob.nnz_adj, "hidden": hidden,
-                       "mode": "2-layer GCN forward on the accelerator + saved-tensor backward, Adam, DP grad all-reduce",
-                       "cuda_graph": bool(use_graph)},
-            "gpu_launches": int(launches), "loss": float(loss.item()),
-        }), flush=True)
+        print(json.dumps(rec), flush=True)
     if world > 1:
         dist.destroy_process_group()

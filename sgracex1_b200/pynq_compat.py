@@ -95,8 +95,10 @@ class RegisterMap:
             self._ignored[name] = int(value)
             return
         value = int(value)
-        if name.endswith("_offset_1") and (value >> 32):
-            self._ip.handle.write_reg64(off, value)      # device pointers are 64-bit
+        if name.endswith("_offset_1"):
+            # device pointers are 64-bit: always write both halves, so that a small value written after a
+            # 64-bit address does not keep the old upper word in *_offset_2
+            self._ip.handle.write_reg64(off, value)
         else:
             self._ip.handle.write_reg(off, value)
 

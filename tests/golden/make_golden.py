@@ -18,6 +18,15 @@ Writes into tests/golden/:
   sym_norm2.npz       inputs + outputs of the reference's sym_norm2 (sgrace.py:18-51)
   ref_hls_*.npz       outputs of the reference HLS source compiled natively (oracle/_ref) on
                       small seeded inputs, so the GPU box can check against the real kernel code
+  real_mol.npz        the reference's own molecule matrices (data/matrices/mol_*.txt, main_float.cpp:40-51:
+                      N 2273, M 7, nnz 5028 / 2273) and the two-layer forward of BASELINE configs[0]
+                      (layer 1 sparse + ReLU, layer 2 dense gemm_mode on layer 1's output) computed by the
+                      reference HLS source (oracle/_ref), HALF and FLOAT builds, hidden 16 and 32
+  real_cora.npz       data/matrices/cora_{adj,feat,weights}.txt (main_float.cpp:73-82) and the layer output of
+                      the reference HLS source, hidden 16, HALF and FLOAT builds
+  real_mutag.npz      jupyter/molecule_gcn/MUTAG/raw/* (the notebook's dataset: 188 graphs, 3371 nodes, 7442
+                      edges, 7 one-hot node labels) and the notebook's two GCN layers (7 -> 64 -> 64, unnormalised
+                      0/1 adjacency without self-loops, cells 16-18) computed by the reference HLS source
 """
 import os
 import re
@@ -223,8 +232,113 @@ def ref_hls():
     print("ref_hls.npz", sorted(k for k in d if "relu" in k))
 
 
+def _kinds():
+    return (("half", O.F16), ("float", O.F32))
+
+
+def real_mol():
+    adj = O.load_csr_txt(MAT + "mol_adj.txt")
+    fea = O.load_csr_txt(MAT + "mol_feat.txt")
+    xd = O.load_dense_txt(MAT + "mol_feat_dense.txt")
+    w = O.load_dense_txt(MAT + "mol_weights.txt")
+    N, M = adj.n, xd.shape[1]
+    assert (N, adj.nnz, fea.nnz, M) == (2273, 5028, 2273, 7) and w.shape[0] == 7    # main_float.cpp:41-45
+    # the dense file is the same matrix as the CSR one
+    chk = np.zeros((N, M), np.float32)
+    for r in range(N):
+        chk[r, fea.col[fea.rowptr[r]:fea.rowptr[r + 1]]] = fea.val[fea.rowptr[r]:fea.rowptr[r + 1]]
+    assert np.array_equal(chk, xd)
+    d = dict(adj_rowptr=adj.rowptr, adj_col=adj.col.astype(np.uint16), adj_val=adj.val,
+             fea_rowptr=fea.rowptr, fea_col=fea.col.astype(np.uint8), fea_val=fea.val, w=w)
+    rng = np.random.default_rng(12345)
+    for P in (16, 32):
+        w2 = rng.uniform(-1.0 / np.sqrt(P), 1.0 / np.sqrt(P), size=(P, P)).astype(np.float32)   # notebook cell 17:53-55
+        d[f"w2_P{P}"] = w2
+        for kind, dt in _kinds():
+            a = (adj.rowptr, adj.col, O.to_storage(adj.val, dt))
+            f = (fea.rowptr, fea.col, O.to_storage(fea.val, dt))
+            B1 = O.to_storage(O.weights_to_B(w[:, :P]), dt)
+            h1 = O.ref_layer(kind=kind, N=N, M_fea=M, P=P, adj=a, B=B1, fea=f, relu=1)
+            h1d = O.ref_layer(kind=kind, N=N, M_fea=M, P=P, adj=a, B=B1, x_dense=O.to_storage(xd, dt), relu=1)
+            B2 = O.to_storage(O.weights_to_B(w2), dt)
+            h2 = O.ref_layer(kind=kind, N=N, M_fea=P, P=P, adj=a, B=B2, x_dense=h1, relu=0)
+            d[f"{kind}_P{P}_layer1"], d[f"{kind}_P{P}_layer1_dense"], d[f"{kind}_P{P}_layer2"] = h1, h1d, h2
+    np.savez_compressed(os.path.join(HERE, "real_mol.npz"), **d)
+    print("real_mol.npz", N, adj.nnz, sorted(k for k in d if "layer" in k))
+
+
+def real_cora():
+    adj = O.load_csr_txt(MAT + "cora_adj.txt")
+    fea = O.load_csr_txt(MAT + "cora_feat.txt")
+    w = O.load_dense_txt(MAT + "cora_weights.txt")
+    N, M, P = adj.n, w.shape[0], 16
+    assert (N, M, adj.nnz, fea.nnz) == (2708, 1433, 13264, 49216)                  # main_float.cpp:74-78
+    fea_one = bool(np.all(fea.val == 1.0))
+    d = dict(adj_rowptr=adj.rowptr, adj_col=adj.col.astype(np.uint16), adj_val=adj.val,
+             fea_rowptr=fea.rowptr, fea_col=fea.col.astype(np.uint16), w=w[:, :P].copy(), fea_all_ones=fea_one)
+    if not fea_one:
+        d["fea_val"] = fea.val
+    for kind, dt in _kinds():
+        a = (adj.rowptr, adj.col, O.to_storage(adj.val, dt))
+        f = (fea.rowptr, fea.col, O.to_storage(fea.val, dt))
+        B = O.to_storage(O.weights_to_B(w[:, :P]), dt)
+        for relu in (0, 1):
+            d[f"{kind}_relu{relu}"] = O.ref_layer(kind=kind, N=N, M_fea=M, P=P, adj=a, B=B, fea=f, relu=relu)
+    np.savez_compressed(os.path.join(HERE, "real_cora.npz"), **d)
+    print("real_cora.npz", N, adj.nnz, fea.nnz, "features all ones:", fea_one)
+
+
+def real_mutag():
+    raw = REF + "/jupyter/molecule_gcn/MUTAG/raw/"
+    edges = np.loadtxt(raw + "MUTAG_A.txt", delimiter=",", dtype=np.int64) - 1        # 1-based (row, col) pairs
+    indicator = np.loadtxt(raw + "MUTAG_graph_indicator.txt", dtype=np.int64) - 1
+    node_labels = np.loadtxt(raw + "MUTAG_node_labels.txt", dtype=np.int64)
+    graph_labels = np.loadtxt(raw + "MUTAG_graph_labels.txt", dtype=np.int64)
+    N, H = len(indicator), 64
+    assert (N, len(edges), len(graph_labels), int(node_labels.max()) + 1) == (3371, 7442, 188, 7)
+    # the notebook's batch of all 188 graphs: dense 0/1 adjacency -> CSR (cell 18:53-56), one-hot x -> CSR (18:94-117)
+    order = np.lexsort((edges[:, 1], edges[:, 0]))
+    e = edges[order]
+    rowptr = np.zeros(N + 1, np.int32)
+    np.add.at(rowptr, e[:, 0] + 1, 1)
+    rowptr = np.cumsum(rowptr).astype(np.int32)
+    col = e[:, 1].astype(np.int32)
+    val = np.ones(len(col), np.float32)
+    frp = np.arange(N + 1, dtype=np.int32)
+    fci = node_labels.astype(np.int32)
+    fva = np.ones(N, np.float32)
+    rng = np.random.default_rng(12345)
+    w1 = rng.uniform(-1.0 / np.sqrt(H), 1.0 / np.sqrt(H), size=(7, H)).astype(np.float32)
+    w2 = rng.uniform(-1.0 / np.sqrt(H), 1.0 / np.sqrt(H), size=(H, H)).astype(np.float32)
+    d = dict(edges=edges.astype(np.int16), graph_indicator=indicator.astype(np.int16), node_labels=node_labels.astype(np.int8),
+             graph_labels=graph_labels.astype(np.int8), w1=w1, w2=w2)
+    for kind, dt in _kinds():
+        a = (rowptr, col, O.to_storage(val, dt))
+        f = (frp, fci, O.to_storage(fva, dt))
+        h1 = O.ref_layer(kind=kind, N=N, M_fea=7, P=H, adj=a, B=O.to_storage(O.weights_to_B(w1), dt), fea=f, relu=1)
+        h2 = O.ref_layer(kind=kind, N=N, M_fea=H, P=H, adj=a, B=O.to_storage(O.weights_to_B(w2), dt), x_dense=h1, relu=0)
+        if kind == "half":
+            d["half_layer1"] = h1
+        d[f"{kind}_layer2"] = h2
+    np.savez_compressed(os.path.join(HERE, "real_mutag.npz"), **d)
+    print("real_mutag.npz", N, len(col))
+
+
+def real_files():
+    if not (O.ref_available("half") and O.ref_available("float")):
+        print("oracle/_ref not built; run `make -C oracle ref` first")
+        return
+    real_mol()
+    real_cora()
+    real_mutag()
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "real":
+        real_files()
+        sys.exit(0)
     citeseer()
     toy()
     ref_hls()
+    real_files()
     qlayers()
