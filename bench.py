@@ -109,6 +109,14 @@ def dist_env():
     return rank, world, local
 
 
+def bench_config(args):
+    """The `config` object of BOTH arms (ours and --impl reference): same workload, same keys, same values."""
+    return {"workload": f"cora_x{args.copies}", "graphs_per_step_per_gpu": args.copies, "nodes_per_graph": 2708,
+            "features": 1433, "hidden": args.hidden or 16, "nnz_adj_per_graph": 13264, "nnz_fea_per_graph": 49216,
+            "mode": "sparse-feature GCN layer D = relu(A.(X.W)), float32",
+            "l2": "inputs 1066 MB per step > 126 MB L2, no flush needed"}
+
+
 def make_cora_batch(copies, seed0, unique=16, P=16):
     from sgracex1_b200 import graphs as G
     probs = [G.cora_shape(seed=seed0 + s, P=P) for s in range(min(unique, copies))]
@@ -152,6 +160,46 @@ def time_cpu(probs, graphs_per_step, steps, warmup, threads):
     return dt / steps, kind
 
 
+def time_cpu_sparse_libs(probs, graphs=64, reps=8):
+    """BASELINE.md section 4 items 2-3 on a block-diagonal batch of `graphs` Cora-shape graphs (how a CPU user
+    would run the same batched layer): the GCNConv-equivalent relu(torch.sparse.mm(A, torch.sparse.mm(X, W))) at one
+    thread and at every host thread, and scipy relu(A @ (X @ W)) (mmult-master.ipynb cell 53).  GTEPS per leg."""
+    import scipy.sparse as sp
+    import torch
+    from sgracex1_b200 import graphs as G
+    b = G.block_diagonal(probs, graphs)
+    W = np.ascontiguousarray(b.B.reshape(b.P, b.M).T)
+    out = []
+
+    def best(fn):
+        fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return float(np.median(ts))
+
+    A = torch.sparse_csr_tensor(torch.from_numpy(b.adj_rowptr.astype(np.int64)), torch.from_numpy(b.adj_col.astype(np.int64)),
+                                torch.from_numpy(b.adj_val), size=(b.N, b.N))
+    X = torch.sparse_csr_tensor(torch.from_numpy(b.fea_rowptr.astype(np.int64)), torch.from_numpy(b.fea_col.astype(np.int64)),
+                                torch.from_numpy(b.fea_val), size=(b.N, b.M))
+    Wt = torch.from_numpy(W)
+    all_threads = os.cpu_count() or 1
+    for th in sorted({1, all_threads}):
+        torch.set_num_threads(th)
+        sec = best(lambda: torch.relu_(torch.sparse.mm(A, torch.sparse.mm(X, Wt))))
+        out.append({"kind": "torch.sparse.mm (GCNConv-equivalent, CSR)", "threads": th, "value": b.nnz_adj / sec / 1e9, "unit": "GTEPS",
+                    "ms_per_graph": sec * 1e3 / graphs, "sample": f"{graphs} graphs block-diagonal, median of {reps}"})
+    torch.set_num_threads(all_threads)
+    As = sp.csr_matrix((b.adj_val, b.adj_col, b.adj_rowptr), shape=(b.N, b.N))
+    Xs = sp.csr_matrix((b.fea_val, b.fea_col, b.fea_rowptr), shape=(b.N, b.M))
+    sec = best(lambda: np.maximum(As @ (Xs @ W), 0.0))
+    out.append({"kind": "scipy csr A @ (X @ W)", "threads": 1, "value": b.nnz_adj / sec / 1e9, "unit": "GTEPS",
+                "ms_per_graph": sec * 1e3 / graphs, "sample": f"{graphs} graphs block-diagonal, median of {reps}"})
+    return out
+
+
 def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
@@ -173,15 +221,90 @@ def run_reference(args):
         "impl": "reference", "metric": "spmm_aggregated_gteps", "value": value, "unit": "GTEPS",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"cora_x{args.copies}", "graphs_per_step": per_step, "nodes": 2708, "features": 1433,
-                   "hidden": args.hidden or 16, "mode": "sparse-feature GCN layer, ReLU"},
+        "config": bench_config(args),
         "cpu_baseline": {"value": value, "unit": "GTEPS", "cores": threads, "kind": kind,
                          "sample": f"{per_step} Cora-shape layers per step ({per_step}/{args.copies} of the workload), "
                                    f"{'reference HLS source compiled natively (oracle/_ref, float build)' if kind == 'reference' else 'oracle port'}"},
         "e2e": {"value": value, "unit": "GTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "graphs_per_s": per_step / sec,
+        "graphs_per_s": per_step / sec, "graphs_per_step_sampled": per_step,
     }
+    try:
+        out["cpu_baseline"]["others"] = time_cpu_sparse_libs(probs)
+    except Exception as ex:  # noqa: BLE001
+        out["cpu_baseline"]["others_error"] = repr(ex)
     print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# further records of the default run (same JSON line): the other BASELINE configs, device-resident
+# ------------------------------------------------------------------------------------------
+def stage_ms(ip, dl, n_rows, reps=5):
+    """CUDA-event time of each stage on the launching stream (inputs resident), best of `reps`."""
+    import torch
+    d, xw = dl.desc, dl.t["XW"].data_ptr()
+    for _ in range(2):
+        ip.handle.fea_run(d, xw)
+        ip.handle.adj_run(d, xw, n_rows)
+    torch.cuda.synchronize()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    best_f = best_a = 1e30
+    for _ in range(reps):
+        e[0].record()
+        ip.handle.fea_run(d, xw)
+        e[1].record()
+        ip.handle.adj_run(d, xw, n_rows)
+        e[2].record()
+        torch.cuda.synchronize()
+        best_f, best_a = min(best_f, e[0].elapsed_time(e[1])), min(best_a, e[1].elapsed_time(e[2]))
+    return best_f, best_a
+
+
+def quantised_records(ip, local, hbm_peak, copies=32):
+    """BASELINE configs[2]: PubMed-shape (x`copies`, block-diagonal) full-design layer -- quantise -> FEA -> rescale ->
+    (GAT edge softmax |) ADJ -> ReLU -> dequantise (demo/sgrace_lib/sgrace.py:563-681) -- at 8 and 4 bits.  Adjacency
+    entries whose code is 0 are the pruned edges (sgrace.py:626-629): skipped in the kernel."""
+    from sgracex1_b200 import _lib, graphs as G, quant as Q
+    from sgracex1_b200.driver import DeviceLayer
+    b = G.block_diagonal([G.pubmed_shape()], copies)
+    att = np.random.default_rng(7).uniform(-0.6, 0.6, size=2 * b.P).astype(np.float32)
+    adj, fea = (b.adj_rowptr, b.adj_col, b.adj_val), (b.fea_rowptr, b.fea_col, b.fea_val)
+    nnz_a, nnz_f = len(adj[1]), len(fea[1])
+    out = {"workload": f"pubmed_x{copies}", "nodes": b.N, "features": b.M, "hidden": b.P, "nnz_adj": nnz_a, "nnz_fea": nnz_f,
+           "note": "device-resident; stage times = CUDA events on the launching stream; GB/s = SURVEY 8d algorithmic bytes / time"}
+    for name, qbits, gat in (("gat_q8", 8, 1), ("gcn_q8", 8, 0), ("gat_q4", 4, 1), ("gcn_q4", 4, 0)):
+        ip.configure(mode=_lib.MODE_FULL, qbits=qbits, staging=0, index_format=0)
+        dl = DeviceLayer(ip.handle, _lib.MODE_FULL, device=f"cuda:{local}")
+        dl.load(N=b.N, M=b.M, P=b.P, adj=adj, fea=fea, B=b.B, relu=1, attention=att, gat_mode=gat, consts=Q.layer_constants(qbits))
+        f_ms, a_ms = stage_ms(ip, dl, b.N)
+        fea_b = (b.N + 1) * 4 + nnz_f * 8 + b.M * b.P * 4 + b.N * b.P * 4
+        adj_b = (b.N + 1) * 4 + nnz_a * 8 + 2 * b.N * b.P * 4 + (2 * nnz_a * 4 + 2 * b.N * 4 if gat else 0)
+        out[name] = {"fea_ms": f_ms, "adj_ms": a_ms, "fea_gbs": fea_b / f_ms / 1e6, "adj_gbs": adj_b / a_ms / 1e6,
+                     "adj_gteps": nnz_a / a_ms / 1e6, "adj_frac_of_hbm_peak": adj_b / a_ms / 1e6 / hbm_peak,
+                     "fea_frac_of_hbm_peak": fea_b / f_ms / 1e6 / hbm_peak}
+        del dl
+    ip.configure(mode=_lib.MODE_F32_FAST, qbits=8, staging=0, index_format=0)
+    return out
+
+
+def csim_record(ip, local, probs, hbm_peak, copies=64):
+    """The mode the drop-in notebook runs in (binary16 buffers, C-simulation accumulate order, bit-exact):
+    Cora-shape x`copies`, device-resident stage times."""
+    from sgracex1_b200 import _lib, graphs as G
+    from sgracex1_b200.driver import DeviceLayer
+    b = G.block_diagonal(probs, copies)
+    ip.configure(mode=_lib.MODE_F16_CSIM, staging=0, index_format=0)
+    dl = DeviceLayer(ip.handle, _lib.MODE_F16_CSIM, device=f"cuda:{local}")
+    to16 = lambda a: np.asarray(a, np.float32).astype(np.float16).view(np.uint16)   # binary16 bit patterns, RNE
+    dl.load(N=b.N, M=b.M, P=b.P, adj=(b.adj_rowptr, b.adj_col, to16(b.adj_val)), fea=(b.fea_rowptr, b.fea_col, to16(b.fea_val)),
+            B=to16(b.B), relu=1)
+    f_ms, a_ms = stage_ms(ip, dl, b.N)
+    ab = b.algorithmic_bytes(elt=2)
+    del dl
+    ip.configure(mode=_lib.MODE_F32_FAST, staging=0, index_format=0)
+    return {"workload": f"cora_x{copies}", "mode": "SGRACE_MODE_F16_CSIM (HALF build order, FADD_LATENCY 4, bit-exact)", "nodes": b.N,
+            "fea_ms": f_ms, "adj_ms": a_ms, "fea_gbs": ab["fea"] / f_ms / 1e6, "adj_gbs": ab["adj"] / a_ms / 1e6,
+            "adj_gteps": b.nnz_adj / a_ms / 1e6, "fea_frac_of_hbm_peak": ab["fea"] / f_ms / 1e6 / hbm_peak,
+            "adj_frac_of_hbm_peak": ab["adj"] / a_ms / 1e6 / hbm_peak}
 
 
 # ------------------------------------------------------------------------------------------
@@ -313,10 +436,9 @@ def run_ours(args):
             "metric": "spmm_aggregated_gteps", "value": value, "unit": "GTEPS", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"cora_x{args.copies}", "graphs_per_step_per_gpu": args.copies, "nodes": batch.N,
-                       "features": batch.M, "hidden": batch.P, "nnz_adj": batch.nnz_adj, "nnz_fea": batch.nnz_fea,
-                       "mode": "sparse-feature GCN layer, ReLU, SGRACE_MODE_F32_FAST",
-                       "l2": f"inputs {ab['layer'] / 1e6:.0f} MB per step > 126 MB L2, no flush needed"},
+            "config": bench_config(args),
+            "workload_detail": {"nodes": batch.N, "nnz_adj": batch.nnz_adj, "nnz_fea": batch.nnz_fea,
+                                "bytes_per_step": ab["layer"], "library_mode": "SGRACE_MODE_F32_FAST"},
             "e2e": {"value": nnz_total / e2e_s / 1e9, "unit": "GTEPS", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "matches_resident": same},
             "gpu_launches": int(launches),
@@ -349,8 +471,40 @@ def run_ours(args):
                                    "sample": f"{sample} of the {args.copies} Cora-shape layers of one step, "
                                              f"{'reference HLS source compiled natively (oracle/_ref float build)' if kind == 'reference' else 'oracle port'}",
                                    "ms_per_graph_per_core": one * 1e3}
-        print(json.dumps(out), flush=True)
+            try:
+                others = time_cpu_sparse_libs(probs)
+                out["cpu_baseline"]["others"] = others
+                legs = [("reference HLS source", out["cpu_baseline"]["value"])] + [(f"{o['kind']} x{o['threads']}", o["value"]) for o in others]
+                out["vs_cpu"] = {name: {"resident_ratio": value / v, "e2e_ratio": out["e2e"]["value"] / v} for name, v in legs}
+            except Exception as ex:  # noqa: BLE001
+                out["cpu_baseline"]["others_error"] = repr(ex)
     hl.free()
+    torch.cuda.set_stream(torch.cuda.default_stream())
+    ip.handle.set_stream(torch.cuda.default_stream().cuda_stream)
+    extra = {}
+    if not args.headline_only:
+        from sgracex1_b200 import dist as sdist, molecule_gcn
+        steps_x = max(5, min(args.steps, 20))
+        if world == 1:
+            for key, fn in (("quantised", lambda: quantised_records(ip, local, hbm_peak)),
+                            ("half_csim", lambda: csim_record(ip, local, probs, hbm_peak))):
+                try:
+                    extra[key] = fn()
+                except Exception as ex:  # noqa: BLE001
+                    extra[key] = {"error": repr(ex)}
+        try:
+            extra["molecule_dp" if world > 1 else "molecule"] = molecule_gcn.molecule_record(steps_x, 3, rank, world, local)
+        except Exception as ex:  # noqa: BLE001
+            extra["molecule"] = {"error": repr(ex)}
+        if world > 1:
+            try:
+                extra["strong"] = sdist.products_strong_record(steps_x, 3, rank, world, local,
+                                                               halo_chunks=int(os.environ.get("SGRACE_HALO_CHUNKS", "1")))
+            except Exception as ex:  # noqa: BLE001
+                extra["strong"] = {"error": repr(ex)}
+    if rank == 0:
+        out.update({k: v for k, v in extra.items() if v is not None})
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -364,6 +518,7 @@ def main():
     ap.add_argument("--workload", default="cora_x1024", choices=["cora_x1024", "products", "molecule"])
     ap.add_argument("--copies", type=int, default=1024, help="Cora-shape graphs per step per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--headline-only", action="store_true", help="skip the extra records (quantised / HALF / molecule / strong scaling)")
     ap.add_argument("--graphs", type=int, default=0, help="molecule workload: graphs per step per GPU (default 188*64)")
     ap.add_argument("--hidden", type=int, default=0, help="hidden width (cora: default 16, the BASELINE config; molecule: default 64)")
     ap.add_argument("--scale", type=float, default=1.0, help="products workload: fraction of the 2.45M-node shape")
