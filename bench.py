@@ -479,9 +479,8 @@ def run_ours(args):
             except Exception as ex:  # noqa: BLE001
                 out["cpu_baseline"]["others_error"] = repr(ex)
     hl.free()
-    torch.cuda.set_stream(torch.cuda.default_stream())
-    ip.handle.set_stream(torch.cuda.default_stream().cuda_stream)
-    extra = {}
+    ip.configure(staging=0)
+    extra = {}                            # the records below run on `stream` too (torch's current stream = the handle's)
     if not args.headline_only:
         from sgracex1_b200 import dist as sdist, molecule_gcn
         steps_x = max(5, min(args.steps, 20))

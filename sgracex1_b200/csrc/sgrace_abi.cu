@@ -278,7 +278,8 @@ int launch_spmm_vec(sgrace_handle* h, const int* rp, const int* ci, const float*
 // b_rows > 0: Bm has b_rows rows and is a candidate for shared-memory staging (FEA: W)
 template <int LPR, int NV>
 int launch_spmm_stream(sgrace_handle* h, const int* rp, const int* ci, const float* va, const float* Bm, float* out,
-                       int nrows, int P, int relu, long long nnz_hint, int b_rows, int final_out, int b_total_rows) {
+                       int nrows, int P, int relu, long long nnz_hint, int b_rows, int final_out, int b_total_rows,
+                       const QConst* qadj = nullptr, int quant = 0) {
     const int P4 = P / 4;
     if (int rc = ensure(h, h->lists, sizeof(int) * (size_t)(nrows > 0 ? nrows : 1))) return rc;
     int *cset, *nset;
@@ -296,6 +297,12 @@ int launch_spmm_stream(sgrace_handle* h, const int* rp, const int* ci, const flo
     sp.long_rows = long_rows; sp.long_count = long_count; sp.tile_counter = tile_counter;
     sp.long_thresh = h->long_row;
     const bool exact = (P4 == LPR * NV);
+    if (qadj) {
+        if (!(exact && NV == 1) || h->peer_count > 0 || h->accumulate)
+            return fail(h, SGRACE_EUNSUPPORTED, "quantised streaming ADJ needs P_w in {4,8,16,32,64,128}");
+        sp.q.inv_as = qadj->inv_as; sp.q.a_z = qadj->a_z; sp.q.qbits = qadj->qbits; sp.q.den = qadj->den;
+        sp.q.deq_o = qadj->deq_o; sp.q.quant = quant;
+    }
 
     // where Bm rows are gathered from: shared memory when the whole matrix fits beside the stages
     if (h->tune.live) load_tune(h);
@@ -333,9 +340,9 @@ int launch_spmm_stream(sgrace_handle* h, const int* rp, const int* ci, const flo
     const size_t smem = stream_smem_bytes(G, S, TR, C, sp.b_bytes);
     if (smem > budget) return fail(h, SGRACE_EUNSUPPORTED, "streaming SpMM needs %zu bytes of shared memory", smem);
 
-#define STREAM_LAUNCH(BS, MT, MB, EX, PEER)                                                                    \
+#define STREAM_LAUNCH(BS, MT, MB, EX, PEER, QA)                                                                \
     do {                                                                                                       \
-        auto kern = spmm_stream_f32_kernel<LPR, NV, BS, MT, MB, EX, PEER>;                                     \
+        auto kern = spmm_stream_f32_kernel<LPR, NV, BS, MT, MB, EX, PEER, QA>;                                 \
         int threads = (BS == BSRC_GLOBAL && MT > 384 && MT < 1024) ? 384 : MT;                                 \
         if ((BS == BSRC_GLOBAL ? tn.threads_g : tn.threads_s) > 0) threads = BS == BSRC_GLOBAL ? tn.threads_g : tn.threads_s; \
         if (threads > MT) threads = MT;                                                                        \
@@ -356,20 +363,29 @@ int launch_spmm_stream(sgrace_handle* h, const int* rp, const int* ci, const flo
     constexpr int MT_SMEM = NV == 1 ? 1024 : 512;
     constexpr int MB_GLOB = NV == 1 ? 2 : 1;
     if (bsrc == BSRC_SMEM) {
-        if (exact) STREAM_LAUNCH(BSRC_SMEM, MT_SMEM, 1, true, false); else STREAM_LAUNCH(BSRC_SMEM, 512, 1, false, false);
+        if (exact) STREAM_LAUNCH(BSRC_SMEM, MT_SMEM, 1, true, false, false); else STREAM_LAUNCH(BSRC_SMEM, 512, 1, false, false, false);
     } else if (h->peer_count > 0) {
         // row-partitioned Bm gathered over NVLink; only wide rows (a full warp per row) are instantiated
         sp.peer_count = h->peer_count; sp.peer_block = h->peer_block;
         for (int r = 0; r < MAX_PEERS; r++) sp.peer_base[r] = h->peer_base[r];
         if (LPR != 32) return fail(h, SGRACE_EUNSUPPORTED, "peer gathers need P_w >= 68 (one warp per row)");
-        if (LPR == 32) { if (exact) STREAM_LAUNCH(BSRC_GLOBAL, 512, MB_GLOB, true, true); else STREAM_LAUNCH(BSRC_GLOBAL, 512, 1, false, true); }
+        if (LPR == 32) { if (exact) STREAM_LAUNCH(BSRC_GLOBAL, 512, MB_GLOB, true, true, false); else STREAM_LAUNCH(BSRC_GLOBAL, 512, 1, false, true, false); }
+    } else if (qadj) {
+        if (NV == 1) STREAM_LAUNCH(BSRC_GLOBAL, 512, 2, true, false, true);
     } else {
-        if (exact) STREAM_LAUNCH(BSRC_GLOBAL, 512, MB_GLOB, true, false); else STREAM_LAUNCH(BSRC_GLOBAL, 512, 1, false, false);
+        if (exact) STREAM_LAUNCH(BSRC_GLOBAL, 512, MB_GLOB, true, false, false); else STREAM_LAUNCH(BSRC_GLOBAL, 512, 1, false, false, false);
     }
 #undef STREAM_LAUNCH
     h->launches++;
     CU(cudaGetLastError());
 
+    if (qadj) {
+        // rows the streaming kernel deferred, in the same multiply-then-add order
+        adj_q_gcn_list_kernel<<<h->num_sms * 2, 256, 0, h->stream>>>(rp, ci, va, Bm, out, long_rows, long_count, P, relu, quant, *qadj, nset);
+        h->launches++;
+        CU(cudaGetLastError());
+        return 0;
+    }
     constexpr int NVL = (LPR * NV + 31) / 32 > 0 ? (LPR * NV + 31) / 32 : 1;
     if (int rc = launch_long_rows<NVL>(h, rp, ci, va, Bm, out, P4, relu, long_rows, long_count, nnz_hint, nset)) return rc;
     return 0;
@@ -679,6 +695,22 @@ int run_adj(sgrace_handle* h, const sgrace_layer_desc* d, const int* rp_adj, con
             const int quant = h->qbits > 0;
             const bool vec = P % 4 == 0 && P <= 1024 && ((((uintptr_t)XW) | ((uintptr_t)d->D)) & 15) == 0;
             if (!d->gat_mode) {
+                // the streaming kernel (TMA-staged CSR slices) with the quantised arithmetic, for the widths whose row
+                // is exactly LPR lanes x one float4
+                const int P4s = P / 4;
+                const bool csr_al = ((((uintptr_t)rp_adj) | ((uintptr_t)d->columnIndex_adj) | ((uintptr_t)d->values_adj)) & 15) == 0;
+                if (vec && csr_al && h->stream_kernel && !h->accumulate && h->peer_count == 0 &&
+                    (P4s == 1 || P4s == 2 || P4s == 4 || P4s == 8 || P4s == 16 || P4s == 32)) {
+#define SGRACE_QSTREAM(L) return launch_spmm_stream<L, 1>(h, rp_adj, d->columnIndex_adj, (const float*)d->values_adj, (const float*)XW, \
+                                                          (float*)d->D, N, P, relu, d->nnz_adj, 0, 1, xw_rows, &qc, quant)
+                    if (P4s == 1) SGRACE_QSTREAM(1);
+                    if (P4s == 2) SGRACE_QSTREAM(2);
+                    if (P4s == 4) SGRACE_QSTREAM(4);
+                    if (P4s == 8) SGRACE_QSTREAM(8);
+                    if (P4s == 16) SGRACE_QSTREAM(16);
+                    SGRACE_QSTREAM(32);
+#undef SGRACE_QSTREAM
+                }
                 if (vec) {
                     const int P4 = P / 4;
 #define SGRACE_ADJQ(L, V) adj_q_gcn_vec_kernel<L, V><<<grid_for((long long)N * L, 256, h->num_sms, 64), 256, 0, h->stream>>>( \

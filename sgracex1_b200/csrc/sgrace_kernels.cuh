@@ -1033,6 +1033,31 @@ fea_q_dense_kernel(const float* __restrict__ X, const signed char* __restrict__ 
 
 // ADJ, quantised GCN: out = relu( sum_k A_q[k] * Wh[col[k],:] ) * deq_o.  Adjacency codes
 // are formed on the fly; zero codes are the pruned edges (S:626-629) and are skipped.
+// The rows the streaming kernel deferred (longer than its threshold): one thread per (listed row, column)
+__global__ void __launch_bounds__(256)
+adj_q_gcn_list_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ val,
+                      const float* __restrict__ Wh, float* __restrict__ out, const int* __restrict__ list,
+                      const int* __restrict__ count, int P, int relu, int quant, QConst qc, int* __restrict__ zero_counters) {
+    const int n = *count;
+    for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < (long long)n * P;
+         gid += (long long)gridDim.x * blockDim.x) {
+        const int r = list[gid / P], j = (int)(gid % P);
+        float acc = 0.f;
+        const int beg = rowptr[r], end = rowptr[r + 1];
+        for (int k = beg; k < end; k++) {
+            float a = __ldg(val + k);
+            if (quant) a = __fdiv_rn((float)q_code_unsigned(a, qc.inv_as, qc.a_z, qc.qbits), qc.den);
+            if (quant && a == 0.f) continue;
+            acc = __fadd_rn(acc, __fmul_rn(a, __ldg(Wh + (size_t)__ldg(col + k) * P + j)));
+        }
+        if (relu && !(acc > 0.f)) acc = 0.f;
+        if (quant) acc = __fmul_rn(acc, qc.deq_o);
+        out[(size_t)r * P + j] = acc;
+    }
+    // the other counter set is zeroed for the next launch (same protocol as the float long-row kernels)
+    if (zero_counters && blockIdx.x == 0 && threadIdx.x < 16) zero_counters[threadIdx.x] = 0;
+}
+
 // One thread per (row, column), float multiply then add in CSR order (the emulation's order).
 __global__ void __launch_bounds__(256)
 adj_q_gcn_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,

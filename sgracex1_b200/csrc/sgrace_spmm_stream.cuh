@@ -40,6 +40,16 @@ namespace sgrace {
 enum { BSRC_GLOBAL = 0, BSRC_SMEM = 1 };
 constexpr int MAX_PEERS = 8;
 
+// quantised full-design ADJ (demo/sgrace_lib/sgrace.py:626-667): adjacency codes formed on the fly, zero codes are
+// pruned edges, float multiply THEN add in CSR order (the emulation's arithmetic), ReLU, dequantise
+struct StreamQ {
+    float inv_as;            // 1 / a_s
+    int a_z, qbits;
+    float den;               // 2^(q-1) (2 for q = 1): a power of two, so the division below is an exact scaling
+    float deq_o;
+    int quant;               // 0: full-design arithmetic without quantisation
+};
+
 struct StreamParams {
     const int* rowptr;
     const int* col;
@@ -63,6 +73,7 @@ struct StreamParams {
     const char* peer_base[MAX_PEERS];
     int peer_block;
     int peer_count;
+    StreamQ q;               // QADJ kernels only
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -112,6 +123,19 @@ __device__ __forceinline__ void fma4s(float4& a, float s, const float4& b) {
     a.z = fmaf(s, b.z, a.z); a.w = fmaf(s, b.w, a.w);
 }
 
+__device__ __forceinline__ void mul_add4s(float4& a, float s, const float4& b) {     // rounded product, rounded sum
+    a.x = __fadd_rn(a.x, __fmul_rn(s, b.x)); a.y = __fadd_rn(a.y, __fmul_rn(s, b.y));
+    a.z = __fadd_rn(a.z, __fmul_rn(s, b.z)); a.w = __fadd_rn(a.w, __fmul_rn(s, b.w));
+}
+// quantization_ufbits (sgrace.py:253-265) / 2^(q-1): torch.round = round-half-even
+__device__ __forceinline__ float stream_adj_code(float x, const StreamQ& q) {
+    float r = rintf(__fadd_rn(__fmul_rn(q.inv_as, x), (float)q.a_z));
+    const float hi = (float)((1 << q.qbits) - 1);
+    r = r < 0.f ? 0.f : r;
+    r = r > hi ? hi : r;
+    return __fmul_rn(r, __frcp_rn(q.den));       // == r / den bit for bit (den is a power of two)
+}
+
 __device__ __forceinline__ float4 relu4(float4 r) {
     r.x = r.x > 0.f ? r.x : 0.f; r.y = r.y > 0.f ? r.y : 0.f;
     r.z = r.z > 0.f ? r.z : 0.f; r.w = r.w > 0.f ? r.w : 0.f;
@@ -135,7 +159,7 @@ inline size_t stream_smem_bytes(int groups, int stages, int tile_rows, int stage
 }
 
 // EXACT: P4 == LPR*NV, so every lane owns live columns and the row stride of Bm is a constant.
-template <int LPR, int NV, int BSRC, int MAXT, int MINB, bool EXACT, bool PEER = false>
+template <int LPR, int NV, int BSRC, int MAXT, int MINB, bool EXACT, bool PEER = false, bool QADJ = false>
 __global__ void __launch_bounds__(MAXT, MINB)
 spmm_stream_f32_kernel(const StreamParams p) {
     constexpr int RPW = 32 / LPR;                 // row groups (= rows in flight) per warp
@@ -373,30 +397,45 @@ spmm_stream_f32_kernel(const StreamParams p) {
                 const int4 c4 = *reinterpret_cast<const int4*>(col_k + kb);
                 const float4 a4 = *reinterpret_cast<const float4*>(val_k + kb);
                 const int cs[4] = {c4.x, c4.y, c4.z, c4.w};
-                const float as[4] = {a4.x, a4.y, a4.z, a4.w};
+                float as[4] = {a4.x, a4.y, a4.z, a4.w};
                 const int lo = beg - kb, hi = end - kb;      // slot s is this row's iff lo <= s < hi
+                bool live[4];
+#pragma unroll
+                for (int s = 0; s < 4; s++) {
+                    live[s] = s >= lo && s < hi;
+                    if (QADJ && p.q.quant) {
+                        as[s] = stream_adj_code(as[s], p.q);
+                        live[s] = live[s] && as[s] != 0.f;       // a zero code is a pruned edge: no gather, no term
+                    }
+                }
                 if (NV <= 2) {
                     // all gathers of the block are issued before any of them is consumed
                     float4 b[4][NV];
 #pragma unroll
                     for (int s = 0; s < 4; s++) {
-                        const bool ok = s >= lo && s < hi;
 #pragma unroll
                         for (int v = 0; v < NV; v++) {
                             b[s][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (ok && (EXACT || v * LPR + l < P4)) b[s][v] = gather(cs[s], v);
+                            if (live[s] && (EXACT || v * LPR + l < P4)) b[s][v] = gather(cs[s], v);
                         }
                     }
 #pragma unroll
                     for (int s = 0; s < 4; s++) {
-                        const float a = (s >= lo && s < hi) ? as[s] : 0.f;
+                        if (QADJ) {
+                            if (live[s]) {
 #pragma unroll
-                        for (int v = 0; v < NV; v++) fma4s(acc[v], a, b[s][v]);
+                                for (int v = 0; v < NV; v++) mul_add4s(acc[v], as[s], b[s][v]);
+                            }
+                        } else {
+                            const float a = live[s] ? as[s] : 0.f;
+#pragma unroll
+                            for (int v = 0; v < NV; v++) fma4s(acc[v], a, b[s][v]);
+                        }
                     }
                 } else {
 #pragma unroll
                     for (int s = 0; s < 4; s++) {
-                        if (s >= lo && s < hi) {
+                        if (live[s]) {
                             float4 b[NV];
 #pragma unroll
                             for (int v = 0; v < NV; v++) {
@@ -404,7 +443,7 @@ spmm_stream_f32_kernel(const StreamParams p) {
                                 if (EXACT || v * LPR + l < P4) b[v] = gather(cs[s], v);
                             }
 #pragma unroll
-                            for (int v = 0; v < NV; v++) fma4s(acc[v], as[s], b[v]);
+                            for (int v = 0; v < NV; v++) { if (QADJ) mul_add4s(acc[v], as[s], b[v]); else fma4s(acc[v], as[s], b[v]); }
                         }
                     }
                 }
@@ -417,6 +456,10 @@ spmm_stream_f32_kernel(const StreamParams p) {
                     float4 r = acc[v];
                     if (p.accumulate) { const float4 o = orow[q]; r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
                     if (p.relu) r = relu4(r);     // val = (acc > 0 || relu == 0) ? acc : 0   (K:2586-2590)
+                    if (QADJ && p.q.quant) {
+                        r.x = __fmul_rn(r.x, p.q.deq_o); r.y = __fmul_rn(r.y, p.q.deq_o);
+                        r.z = __fmul_rn(r.z, p.q.deq_o); r.w = __fmul_rn(r.w, p.q.deq_o);
+                    }
                     if (p.streaming_store) __stcs(orow + q, r); else orow[q] = r;
                 }
             }
