@@ -363,17 +363,17 @@ int launch_spmm_stream(sgrace_handle* h, const int* rp, const int* ci, const flo
     constexpr int MT_SMEM = NV == 1 ? 1024 : 512;
     constexpr int MB_GLOB = NV == 1 ? 2 : 1;
     if (bsrc == BSRC_SMEM) {
-        if (exact) STREAM_LAUNCH(BSRC_SMEM, MT_SMEM, 1, true, false, false); else STREAM_LAUNCH(BSRC_SMEM, 512, 1, false, false, false);
+        if (exact) STREAM_LAUNCH(BSRC_SMEM, MT_SMEM, 1, true, false, QM_NONE); else STREAM_LAUNCH(BSRC_SMEM, 512, 1, false, false, QM_NONE);
     } else if (h->peer_count > 0) {
         // row-partitioned Bm gathered over NVLink; only wide rows (a full warp per row) are instantiated
         sp.peer_count = h->peer_count; sp.peer_block = h->peer_block;
         for (int r = 0; r < MAX_PEERS; r++) sp.peer_base[r] = h->peer_base[r];
         if (LPR != 32) return fail(h, SGRACE_EUNSUPPORTED, "peer gathers need P_w >= 68 (one warp per row)");
-        if (LPR == 32) { if (exact) STREAM_LAUNCH(BSRC_GLOBAL, 512, MB_GLOB, true, true, false); else STREAM_LAUNCH(BSRC_GLOBAL, 512, 1, false, true, false); }
+        if (LPR == 32) { if (exact) STREAM_LAUNCH(BSRC_GLOBAL, 512, MB_GLOB, true, true, QM_NONE); else STREAM_LAUNCH(BSRC_GLOBAL, 512, 1, false, true, QM_NONE); }
     } else if (qadj) {
-        if (NV == 1) STREAM_LAUNCH(BSRC_GLOBAL, 512, 2, true, false, true);
+        if (NV == 1) STREAM_LAUNCH(BSRC_GLOBAL, 512, 2, true, false, QM_GCN);
     } else {
-        if (exact) STREAM_LAUNCH(BSRC_GLOBAL, 512, MB_GLOB, true, false, false); else STREAM_LAUNCH(BSRC_GLOBAL, 512, 1, false, false, false);
+        if (exact) STREAM_LAUNCH(BSRC_GLOBAL, 512, MB_GLOB, true, false, QM_NONE); else STREAM_LAUNCH(BSRC_GLOBAL, 512, 1, false, false, QM_NONE);
     }
 #undef STREAM_LAUNCH
     h->launches++;

@@ -1309,20 +1309,66 @@ gat_aggregate_vec_kernel(const int* __restrict__ rowptr, const int* __restrict__
     if (row >= nrows) return;
     const int beg = rowptr[row], end = rowptr[row + 1];
     const float si = s1[row0 + row];              // row0: global index of local row 0 (row-partitioned GAT)
+    // The first KC edges of every lane (rows of up to KC*LPR edges: most of a citation graph) keep their column and
+    // logit in registers, so the adjacency value, the column index and the source score are loaded once instead of
+    // once per pass; longer rows recompute the rest.  The arithmetic and its order are those of the three-pass form.
+    constexpr int KC = 2;
+    int cr[KC];                                   // column of the cached edge, -1: pruned / outside the row
+    float er[KC];
+    auto logit = [&](int k, int& c) -> float {    // NaN-free: returns 0 and c = -1 for a pruned edge
+        float a = __ldg(val + k);
+        if (quant) a = (float)q_code_unsigned(a, qc.inv_as, qc.a_z, qc.qbits);
+        c = -1;
+        if (!(a > 0.f)) return 0.f;
+        c = __ldg(col + k);
+        const float e = __fadd_rn(si, __ldg(s2 + c));
+        return e > 0.f ? e : __fmul_rn(qc.alpha, e);
+    };
+    // four edges of this lane at once (k, k + LPR, ...): the three dependent loads of an edge (value -> column ->
+    // source score) are issued for all four before any is consumed.  A hub row (172 edges on the PubMed shape) is
+    // otherwise a serial chain of ~130 round trips per pass that the whole launch waits for.
+    auto logit4 = [&](int k, int (&c)[4], float (&e)[4]) {
+        float a[4], sv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int kk = k + u * LPR;
+            a[u] = kk < end ? __ldg(val + kk) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (quant) a[u] = (float)q_code_unsigned(a[u], qc.inv_as, qc.a_z, qc.qbits);
+            c[u] = (k + u * LPR < end && a[u] > 0.f) ? __ldg(col + k + u * LPR) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) sv[u] = c[u] >= 0 ? __ldg(s2 + c[u]) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const float t = __fadd_rn(si, sv[u]);
+            e[u] = c[u] >= 0 ? (t > 0.f ? t : __fmul_rn(qc.alpha, t)) : 0.f;
+        }
+    };
     // logits, row maximum, surviving-edge count
     float mx = -INFINITY;
     int live = 0;
-    for (int k = beg + l; k < end; k += LPR) {
-        float a = __ldg(val + k);
-        if (quant) a = (float)q_code_unsigned(a, qc.inv_as, qc.a_z, qc.qbits);
-        float e = 0.f;
-        if (a > 0.f) {
-            e = __fadd_rn(si, __ldg(s2 + __ldg(col + k)));
-            e = e > 0.f ? e : __fmul_rn(qc.alpha, e);
-            mx = fmaxf(mx, e);
-            live++;
+#pragma unroll
+    for (int i = 0; i < KC; i++) {
+        const int k = beg + l + i * LPR;
+        cr[i] = -1; er[i] = 0.f;
+        if (k < end) {
+            er[i] = logit(k, cr[i]);
+            if (cr[i] >= 0) { mx = fmaxf(mx, er[i]); live++; }
+            if (E) E[k] = er[i];
         }
-        if (E) E[k] = e;
+    }
+    for (int k = beg + l + KC * LPR; k < end; k += 4 * LPR) {
+        int c[4];
+        float e[4];
+        logit4(k, c, e);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (c[u] >= 0) { mx = fmaxf(mx, e[u]); live++; }
+            if (E && k + u * LPR < end) E[k + u * LPR] = e[u];
+        }
     }
 #pragma unroll
     for (int off = 1; off < LPR; off <<= 1) {
@@ -1335,14 +1381,16 @@ gat_aggregate_vec_kernel(const int* __restrict__ rowptr, const int* __restrict__
         return;
     }
     float sum = 0.f;
-    for (int k = beg + l; k < end; k += LPR) {
-        float a = __ldg(val + k);
-        if (quant) a = (float)q_code_unsigned(a, qc.inv_as, qc.a_z, qc.qbits);
-        if (a > 0.f) {
-            float e = __fadd_rn(si, __ldg(s2 + __ldg(col + k)));
-            e = e > 0.f ? e : __fmul_rn(qc.alpha, e);
-            sum += expf(e - mx);
-        }
+#pragma unroll
+    for (int i = 0; i < KC; i++)
+        if (cr[i] >= 0) sum += expf(er[i] - mx);
+    for (int k = beg + l + KC * LPR; k < end; k += 4 * LPR) {
+        int c[4];
+        float e[4];
+        logit4(k, c, e);
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (c[u] >= 0) sum += expf(e[u] - mx);
     }
 #pragma unroll
     for (int off = 1; off < LPR; off <<= 1) sum += __shfl_xor_sync(gmask, sum, off);
@@ -1350,22 +1398,10 @@ gat_aggregate_vec_kernel(const int* __restrict__ rowptr, const int* __restrict__
     float4 acc[NV];
 #pragma unroll
     for (int v = 0; v < NV; v++) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int k0 = beg; k0 < end; k0 += LPR) {
-        const int k = k0 + l;
-        int c = 0;
-        float s = 0.f;
-        if (k < end) {
-            float a = __ldg(val + k);
-            if (quant) a = (float)q_code_unsigned(a, qc.inv_as, qc.a_z, qc.qbits);
-            if (a > 0.f) {
-                c = __ldg(col + k);
-                float e = __fadd_rn(si, __ldg(s2 + c));
-                e = e > 0.f ? e : __fmul_rn(qc.alpha, e);
-                s = expf(e - mx) / sum;
-            }
-            if (S) S[k] = s;
-        }
+    // one round = the LPR edges k0 .. k0+LPR-1; this lane owns edge k0 + l with column c (>= 0) and weight s
+    auto round = [&](int k0, int c, float s) {
         const int cnt = min(LPR, end - k0);
+        if (c < 0) { c = 0; s = 0.f; }
         for (int i0 = 0; i0 < cnt; i0 += 4) {
             int cc[4]; float ss[4]; float4 b[4][NV];
 #pragma unroll
@@ -1386,6 +1422,30 @@ gat_aggregate_vec_kernel(const int* __restrict__ rowptr, const int* __restrict__
             for (int i = 0; i < 4; i++)
 #pragma unroll
                 for (int v = 0; v < NV; v++) fma4(acc[v], ss[i], b[i][v]);
+        }
+    };
+#pragma unroll
+    for (int i = 0; i < KC; i++) {
+        const int k0 = beg + i * LPR;
+        if (k0 < end) {                               // uniform over the row group
+            const int k = k0 + l;
+            const float s = cr[i] >= 0 ? expf(er[i] - mx) / sum : 0.f;
+            if (S && k < end) S[k] = s;
+            round(k0, cr[i], s);
+        }
+    }
+    for (int k0 = beg + KC * LPR; k0 < end; k0 += 4 * LPR) {
+        int c[4];
+        float e[4];
+        logit4(k0 + l, c, e);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int kk0 = k0 + u * LPR;
+            if (kk0 < end) {                          // uniform over the row group
+                const float s = c[u] >= 0 ? expf(e[u] - mx) / sum : 0.f;
+                if (S && kk0 + l < end) S[kk0 + l] = s;
+                round(kk0, c[u], s);
+            }
         }
     }
 #pragma unroll

@@ -49,6 +49,7 @@ struct StreamQ {
     float deq_o;
     int quant;               // 0: full-design arithmetic without quantisation
 };
+enum { QM_NONE = 0, QM_GCN = 1 };
 
 struct StreamParams {
     const int* rowptr;
@@ -73,7 +74,7 @@ struct StreamParams {
     const char* peer_base[MAX_PEERS];
     int peer_block;
     int peer_count;
-    StreamQ q;               // QADJ kernels only
+    StreamQ q;               // QM_GCN kernels only
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -159,7 +160,7 @@ inline size_t stream_smem_bytes(int groups, int stages, int tile_rows, int stage
 }
 
 // EXACT: P4 == LPR*NV, so every lane owns live columns and the row stride of Bm is a constant.
-template <int LPR, int NV, int BSRC, int MAXT, int MINB, bool EXACT, bool PEER = false, bool QADJ = false>
+template <int LPR, int NV, int BSRC, int MAXT, int MINB, bool EXACT, bool PEER = false, int QM = QM_NONE>
 __global__ void __launch_bounds__(MAXT, MINB)
 spmm_stream_f32_kernel(const StreamParams p) {
     constexpr int RPW = 32 / LPR;                 // row groups (= rows in flight) per warp
@@ -403,7 +404,7 @@ spmm_stream_f32_kernel(const StreamParams p) {
 #pragma unroll
                 for (int s = 0; s < 4; s++) {
                     live[s] = s >= lo && s < hi;
-                    if (QADJ && p.q.quant) {
+                    if (QM == QM_GCN && p.q.quant) {
                         as[s] = stream_adj_code(as[s], p.q);
                         live[s] = live[s] && as[s] != 0.f;       // a zero code is a pruned edge: no gather, no term
                     }
@@ -421,7 +422,7 @@ spmm_stream_f32_kernel(const StreamParams p) {
                     }
 #pragma unroll
                     for (int s = 0; s < 4; s++) {
-                        if (QADJ) {
+                        if (QM == QM_GCN) {
                             if (live[s]) {
 #pragma unroll
                                 for (int v = 0; v < NV; v++) mul_add4s(acc[v], as[s], b[s][v]);
@@ -443,7 +444,7 @@ spmm_stream_f32_kernel(const StreamParams p) {
                                 if (EXACT || v * LPR + l < P4) b[v] = gather(cs[s], v);
                             }
 #pragma unroll
-                            for (int v = 0; v < NV; v++) { if (QADJ) mul_add4s(acc[v], as[s], b[v]); else fma4s(acc[v], as[s], b[v]); }
+                            for (int v = 0; v < NV; v++) { if (QM == QM_GCN) mul_add4s(acc[v], as[s], b[v]); else fma4s(acc[v], as[s], b[v]); }
                         }
                     }
                 }
@@ -456,7 +457,7 @@ spmm_stream_f32_kernel(const StreamParams p) {
                     float4 r = acc[v];
                     if (p.accumulate) { const float4 o = orow[q]; r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
                     if (p.relu) r = relu4(r);     // val = (acc > 0 || relu == 0) ? acc : 0   (K:2586-2590)
-                    if (QADJ && p.q.quant) {
+                    if (QM == QM_GCN && p.q.quant) {
                         r.x = __fmul_rn(r.x, p.q.deq_o); r.y = __fmul_rn(r.y, p.q.deq_o);
                         r.z = __fmul_rn(r.z, p.q.deq_o); r.w = __fmul_rn(r.w, p.q.deq_o);
                     }

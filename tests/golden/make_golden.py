@@ -24,6 +24,10 @@ Writes into tests/golden/:
                       reference HLS source (oracle/_ref), HALF and FLOAT builds, hidden 16 and 32
   real_cora.npz       data/matrices/cora_{adj,feat,weights}.txt (main_float.cpp:73-82) and the layer output of
                       the reference HLS source, hidden 16, HALF and FLOAT builds
+  demo_model_cora.npz the reference's demo model (GAT_PYNQ: att2 -> Relu_SGRACE -> conv22 -> Linear) composed from the
+                      reference's unmodified sgrace.py pieces, emulation mode, on the real Cora files: seeded
+                      parameters, both layer outputs and the logits, 8- and 4-bit, GCN and GAT; and the state_dict keys
+                      of demo/zcu104/model_Photo_8bit.ptx
   real_mutag.npz      jupyter/molecule_gcn/MUTAG/raw/* (the notebook's dataset: 188 graphs, 3371 nodes, 7442
                       edges, 7 one-hot node labels) and the notebook's two GCN layers (7 -> 64 -> 64, unnormalised
                       0/1 adjacency without self-loops, cells 16-18) computed by the reference HLS source
@@ -324,6 +328,56 @@ def real_mutag():
     print("real_mutag.npz", N, len(col))
 
 
+def demo_model():
+    """The reference's demo model (demo/emulation/demo_sgrace.py:271-401, GAT_PYNQ) on the reference's own Cora
+    files, in the emulation mode (acc = 0): the class cannot be imported (the script loads Planetoid at import), so
+    its forward is composed here from the reference's own, unmodified pieces -- sym_norm2, GATConv_SGRACE,
+    Relu_SGRACE from demo/sgrace_lib/sgrace.py -- in the order of demo_sgrace.py:292-399."""
+    adj = O.load_csr_txt(MAT + "cora_adj.txt")
+    fea = O.load_csr_txt(MAT + "cora_feat.txt")
+    n, m, hidden, classes = adj.n, 1433, 16, 7
+    rows = np.repeat(np.arange(n), np.diff(adj.rowptr))
+    keep = rows != adj.col                               # the file holds A + I normalised; the model wants the raw edges
+    ei = np.stack([rows[keep], adj.col[keep]]).astype(np.int64)
+    assert ei.shape[1] == 10556
+    x = np.zeros((n, m), np.float32)
+    x[np.repeat(np.arange(n), np.diff(fea.rowptr)), fea.col] = fea.val
+    avg_deg = ei.shape[1] / n
+    fill = int(np.trunc(np.log2(avg_deg)))
+    d = dict(edge_index=ei.astype(np.int32), fea_rowptr=fea.rowptr, fea_col=fea.col.astype(np.uint16), average_node_degree=avg_deg,
+             state_dict_keys=np.array(["att2.weight", "att2.attention", "att2.bias", "conv22.weight", "conv22.attention",
+                                       "conv22.bias", "lin.weight", "lin.bias"]))
+    import torch.nn.functional as F
+    for qbits in (8, 4):
+        for gat in (0, 1):
+            config, sg = import_reference_sgrace(qbits, gat)
+            torch.manual_seed(12345)
+            att2 = sg.GATConv_SGRACE(m, hidden, 1, dropout=0.1, alpha=0.2, concat=False)
+            conv22 = sg.GATConv_SGRACE(hidden, hidden, 1)
+            reluh = sg.Relu_SGRACE()
+            lin = torch.nn.Linear(hidden, classes)
+            if qbits == 8 and gat == 0:
+                for k, v in (("att2.weight", att2.weight), ("att2.attention", att2.attention), ("conv22.weight", conv22.weight),
+                             ("conv22.attention", conv22.attention), ("lin.weight", lin.weight), ("lin.bias", lin.bias)):
+                    d["p_" + k] = v.detach().numpy().copy()
+            with torch.no_grad():
+                xt = torch.from_numpy(x)
+                edge_index, norm = sg.sym_norm2(torch.from_numpy(ei), n, None, fill, torch.float32)
+                a = torch.sparse_coo_tensor(edge_index, norm, (n, n))
+                h1 = att2.forward(gat, 0, 1, xt, edge_index, norm, a)
+                h1 = reluh(h1)
+                h2 = conv22.forward(gat, 1, 0, h1, edge_index, norm, a)
+                out = lin(h2.float())                      # eval mode: dropout is the identity
+            if qbits == 8:
+                d[f"q{qbits}_gat{gat}_h1"] = h1.numpy().astype(np.float32)
+            d[f"q{qbits}_gat{gat}_h2"] = h2.numpy().astype(np.float32)
+            d[f"q{qbits}_gat{gat}_logits"] = out.numpy().astype(np.float32)
+            print(f"demo model q{qbits} gat{gat}: |h2| {float(np.abs(d[f'q{qbits}_gat{gat}_h2']).max()):.4f} "
+                  f"|logits| {float(np.abs(d[f'q{qbits}_gat{gat}_logits']).max()):.4f}")
+    np.savez_compressed(os.path.join(HERE, "demo_model_cora.npz"), **d)
+    print("demo_model_cora.npz")
+
+
 def real_files():
     if not (O.ref_available("half") and O.ref_available("float")):
         print("oracle/_ref not built; run `make -C oracle ref` first")
@@ -337,8 +391,12 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "real":
         real_files()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "demo":
+        demo_model()
+        sys.exit(0)
     citeseer()
     toy()
     ref_hls()
     real_files()
+    demo_model()
     qlayers()
