@@ -251,6 +251,21 @@ int sgrace_sym_norm(sgrace_handle* h, const int32_t* row, const int32_t* col, co
 int sgrace_dense_to_csr(sgrace_handle* h, const float* X, int32_t n, int32_t m, int64_t capacity, int32_t* rowptr,
                         int32_t* col, float* val, int64_t* out_nnz);
 
+/* sgrace_prune_adjacency: the adaptive pruning of the full design made explicit.  The quantiser maps small adjacency
+ * entries to code 0 (quantization_ufbits, demo/sgrace_lib/sgrace.py:253-265, applied at :626-629; "adaptive
+ * pruning", demo/emulation/demo_sgrace.py:32-36) and a zero code contributes nothing to the aggregation or to the
+ * GAT softmax (mask at :640).  This call drops those entries once, on the device: CSR in (rowptr n + 1, col / val
+ * nnz, device), CSR out (out_rowptr n + 1; out_col / out_val with room for nnz entries), survivors in their original
+ * order with their ORIGINAL float values, so a layer run on the compacted arrays quantises them to the same non-zero
+ * codes while streaming fewer bytes: the GCN aggregation returns the same D bit for bit, the GAT one the same
+ * logits E and, because its softmax sums are grouped by edge position, the same S / D to rounding.  `kept` (optional, nnz ints) receives the
+ * input index of every survivor (E / S of a GAT layer on the compacted graph map back through it).  qscale_adj =
+ * 1 / a_s as written to quantization_scale_adj; the zero point is 0 as the driver programs it.  Synchronises the
+ * handle's stream (*out_nnz is returned to the host). */
+int sgrace_prune_adjacency(sgrace_handle* h, const int32_t* rowptr, const int32_t* col, const float* val, int32_t n, int64_t nnz,
+                           float qscale_adj, int32_t qbits, int32_t* out_rowptr, int32_t* out_col, float* out_val, int32_t* kept,
+                           int64_t* out_nnz);
+
 /* number of this library's kernels launched on the handle since creation (bench evidence) */
 int sgrace_launch_count(sgrace_handle* h, uint64_t* count);
 

@@ -23,7 +23,7 @@ EXPORTS = (
     "sgrace_read_reg", "sgrace_write_reg64", "sgrace_reg_offset", "sgrace_set_option",
     "sgrace_get_option", "sgrace_set_stream", "sgrace_start", "sgrace_done", "sgrace_wait",
     "sgrace_stage_times", "sgrace_layer_run", "sgrace_fea_run", "sgrace_adj_run",
-    "sgrace_launch_count", "sgrace_dense_run", "sgrace_peer_alloc", "sgrace_peer_open", "sgrace_peer_close", "sgrace_peer_release",
+    "sgrace_launch_count", "sgrace_dense_run", "sgrace_peer_alloc", "sgrace_peer_open", "sgrace_peer_close", "sgrace_peer_release", "sgrace_prune_adjacency",
     "sgrace_adj_run_peer", "sgrace_halo_gather", "sgrace_halo_push", "sgrace_xty_run",
     "sgrace_peer_copy", "sgrace_peer_signal", "sgrace_wait_flag", "sgrace_sym_norm", "sgrace_dense_to_csr",
 )
@@ -105,6 +105,8 @@ def load():
     lib.sgrace_dense_to_csr.argtypes = [H, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.POINTER(C.c_int64)]
     lib.sgrace_xty_run.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
+    lib.sgrace_prune_adjacency.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_int32,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
     lib.sgrace_dense_run.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     for name in EXPORTS:
         if name not in ("sgrace_last_error", "sgrace_version"):
@@ -278,6 +280,15 @@ class Handle:
         if rc not in (0, -5):
             self._ck(rc)
         return rc, int(k.value)
+
+    def prune_adjacency(self, rowptr, col, val, n, nnz, qscale_adj, qbits, out_rowptr, out_col, out_val, kept=0):
+        """sgrace_prune_adjacency (device pointers); returns the number of surviving non-zeros."""
+        k = C.c_int64()
+        self._ck(self.lib.sgrace_prune_adjacency(self.h, C.c_void_p(rowptr), C.c_void_p(col or None), C.c_void_p(val or None), int(n),
+                                                 int(nnz), C.c_float(qscale_adj), int(qbits), C.c_void_p(out_rowptr),
+                                                 C.c_void_p(out_col or None), C.c_void_p(out_val or None), C.c_void_p(kept or None),
+                                                 C.byref(k)))
+        return int(k.value)
 
     def xty_run(self, x_ptr, y_ptr, out_ptr, N, M, P):
         self._ck(self.lib.sgrace_xty_run(self.h, C.c_void_p(x_ptr), C.c_void_p(y_ptr), C.c_void_p(out_ptr), int(N), int(M), int(P)))

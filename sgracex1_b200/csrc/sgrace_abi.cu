@@ -486,6 +486,22 @@ int stage_exact_any(sgrace_handle* h, int mode, int lat, const int* rp, const in
         case SGRACE_MODE_F32_CSIM:
             return stage_exact<OpsF32>(h, lat, rp, ci, va, Bm, out, nrows, P, hw_threads, sblock, dense_M, relu);
         case SGRACE_MODE_F16_CSIM:
+            if (P % 2 == 0 && ((((uintptr_t)Bm) | ((uintptr_t)out)) & 3) == 0 && nrows > 0 && lat >= 1 && lat <= 8) {
+                // two columns per thread on the packed half pipes, same order bit for bit
+                const long long items = (long long)nrows * (P / 2);
+                const long long g = (items + 255) / 256;
+                if (g > 0x7fffffffLL) return fail(h, SGRACE_EUNSUPPORTED, "problem too large for exact kernel");
+#define LAUNCH_X2(L) stage_exact_f16x2_kernel<L><<<(int)g, 256, 0, h->stream>>>(rp, ci, (const unsigned short*)va, (const unsigned*)Bm, \
+                                                                                 (unsigned*)out, nrows, P / 2, hw_threads, sblock, dense_M, relu)
+                switch (lat) {
+                    case 1: LAUNCH_X2(1); break; case 2: LAUNCH_X2(2); break; case 3: LAUNCH_X2(3); break; case 4: LAUNCH_X2(4); break;
+                    case 5: LAUNCH_X2(5); break; case 6: LAUNCH_X2(6); break; case 7: LAUNCH_X2(7); break; default: LAUNCH_X2(8); break;
+                }
+#undef LAUNCH_X2
+                h->launches++;
+                CU(cudaGetLastError());
+                return 0;
+            }
             return stage_exact<OpsF16>(h, lat, rp, ci, va, Bm, out, nrows, P, hw_threads, sblock, dense_M, relu);
         case SGRACE_MODE_FIX16_CSIM:
             return stage_exact<OpsFix16>(h, 1, rp, ci, va, Bm, out, nrows, P, hw_threads, sblock, dense_M, relu);
@@ -1692,6 +1708,42 @@ int sgrace_dense_to_csr(sgrace_handle* h, const float* X, int32_t n, int32_t m, 
     dense_fill_kernel<<<blocks, 256, 0, h->stream>>>(X, n, m, rowptr, capacity, col, val);
     CU(cudaGetLastError());
     h->launches++;
+    return SGRACE_OK;
+}
+
+int sgrace_prune_adjacency(sgrace_handle* h, const int32_t* rowptr, const int32_t* col, const float* val, int32_t n, int64_t nnz,
+                           float qscale_adj, int32_t qbits, int32_t* out_rowptr, int32_t* out_col, float* out_val, int32_t* kept,
+                           int64_t* out_nnz) {
+    if (!h) return SGRACE_EINVAL;
+    h->last_status = 0;
+    CU(cudaSetDevice(h->device));
+    if (n < 0 || nnz < 0 || nnz >= 0x7fffffffLL || !rowptr || !out_rowptr || !out_nnz || (nnz > 0 && (!col || !val || !out_col || !out_val)))
+        return fail(h, SGRACE_EINVAL, "prune_adjacency: bad argument");
+    if (qbits < 1 || qbits > 8 || !(qscale_adj > 0.f)) return fail(h, SGRACE_EINVAL, "prune_adjacency: qbits in 1..8 and a positive scale");
+    using namespace prep;
+    *out_nnz = 0;
+    const size_t pos_bytes = sizeof(int) * ((size_t)nnz + 1);
+    if (int rc = ensure(h, h->prep_ids, pos_bytes)) return rc;
+    int* pos = (int*)h->prep_ids.p;
+    const int blocks = (int)((nnz + 1 + 255) / 256);
+    prune_flag_kernel<<<blocks, 256, 0, h->stream>>>(val, nnz, qscale_adj, 0, qbits, pos);
+    CU(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, pos, pos, (int)(nnz + 1), h->stream));
+    if (int rc = ensure(h, h->prep_tmp, tmp_bytes)) return rc;
+    tmp_bytes = h->prep_tmp.bytes;
+    CU(cub::DeviceScan::ExclusiveSum(h->prep_tmp.p, tmp_bytes, pos, pos, (int)(nnz + 1), h->stream));
+    if (nnz > 0) {
+        prune_scatter_kernel<<<(int)((nnz + 255) / 256), 256, 0, h->stream>>>(col, val, pos, nnz, out_col, out_val, kept);
+        CU(cudaGetLastError());
+    }
+    prune_rowptr_kernel<<<(n + 1 + 255) / 256, 256, 0, h->stream>>>(rowptr, pos, n, out_rowptr);
+    CU(cudaGetLastError());
+    int total = 0;
+    CU(cudaMemcpyAsync(&total, pos + nnz, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    *out_nnz = total;
+    h->launches += 4;
     return SGRACE_OK;
 }
 

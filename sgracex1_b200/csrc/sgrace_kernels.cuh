@@ -871,7 +871,12 @@ stage_exact_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
     typedef typename Ops::T T;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)nrows * P) return;
-    const int r = (int)(gid / P), j = (int)(gid % P);
+    int r, j;
+    if ((long long)nrows * P < 0x7fffffffLL) {
+        r = (int)((unsigned)gid / (unsigned)P); j = (int)((unsigned)gid - (unsigned)r * (unsigned)P);
+    } else {
+        r = (int)(gid / P); j = (int)(gid % P);
+    }
     // hardware-thread slice and sblock that contain row r
     const int blk = nrows / hw_threads;
     int t = blk > 0 ? r / blk : hw_threads - 1;
@@ -887,7 +892,7 @@ stage_exact_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
     T part[LAT];
 #pragma unroll
     for (int i = 0; i < LAT; i++) part[i] = Ops::zero();
-    int lane = (int)((beg - base) % LAT);
+    int lane = (beg - base) < 0x7fffffffLL ? (int)((unsigned)(beg - base) % (unsigned)LAT) : (int)((beg - base) % LAT);
     for (long long k = beg; k < end; k++) {
         const T v = val[k];
         const long long ci = dense_M > 0 ? (k - beg) : (long long)col[k];
@@ -902,6 +907,73 @@ stage_exact_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
     for (int i = 1; i < LAT; i++) acc = Ops::add(acc, part[i]);
     if (relu && !Ops::gt0(acc)) acc = Ops::zero();
     out[(long long)r * P + j] = acc;
+}
+
+// HALF build, two output columns per thread on the packed half pipes (HMUL2 / HADD2): the same stream walk, lane
+// rotation and fold order as stage_exact_kernel<OpsF16, LAT>, bit for bit.  The native binary16 multiply / add round
+// the exact result to nearest-even with gradual underflow; the spacing of the subnormals equals the spacing of the
+// lowest normal binade, so "round, then flush a subnormal result" (the Xilinx operator, see OpsF16) is the native
+// result with its subnormals flushed.  Operands are flushed when loaded; every stored partial sum is already flushed.
+__device__ __forceinline__ unsigned ftz_h2(unsigned x) {
+    // a half whose exponent field is zero reads as a signed zero
+    return x & (__vcmpne2(x & 0x7c007c00u, 0u) | 0x80008000u);
+}
+__device__ __forceinline__ unsigned h2_mul(unsigned a, unsigned b) {
+    const __half2 r = __hmul2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return ftz_h2(*reinterpret_cast<const unsigned*>(&r));
+}
+__device__ __forceinline__ unsigned h2_add(unsigned a, unsigned b) {
+    const __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return ftz_h2(*reinterpret_cast<const unsigned*>(&r));
+}
+
+template <int LAT>
+__global__ void __launch_bounds__(256)
+stage_exact_f16x2_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const unsigned short* __restrict__ val,
+                         const unsigned* __restrict__ Bm2,     // row-major, P/2 packed pairs per row
+                         unsigned* __restrict__ out2, int nrows, int P2, int hw_threads, int sblock, int dense_M, int relu) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)nrows * P2) return;
+    int r, j;                                          // 32-bit division whenever the index fits (the 64-bit one costs
+    if ((long long)nrows * P2 < 0x7fffffffLL) {        // more than a short row's arithmetic)
+        r = (int)((unsigned)gid / (unsigned)P2); j = (int)((unsigned)gid - (unsigned)r * (unsigned)P2);
+    } else {
+        r = (int)(gid / P2); j = (int)(gid % P2);
+    }
+    const int blk = nrows / hw_threads;
+    int t = blk > 0 ? r / blk : hw_threads - 1;
+    if (t > hw_threads - 1) t = hw_threads - 1;
+    const int first_row = t * blk;
+    const int base_row = first_row + ((r - first_row) / sblock) * sblock;
+    long long beg, end, base;
+    if (dense_M > 0) {
+        beg = (long long)r * dense_M; end = beg + dense_M; base = (long long)base_row * dense_M;
+    } else {
+        beg = rowptr[r]; end = rowptr[r + 1]; base = rowptr[base_row];
+    }
+    unsigned part[LAT];
+#pragma unroll
+    for (int i = 0; i < LAT; i++) part[i] = 0u;
+    int lane = (beg - base) < 0x7fffffffLL ? (int)((unsigned)(beg - base) % (unsigned)LAT) : (int)((beg - base) % LAT);
+    for (long long k = beg; k < end; k++) {
+        const unsigned v = (unsigned)OpsF16::ftz(val[k]);
+        const long long ci = dense_M > 0 ? (k - beg) : (long long)col[k];
+        const unsigned prod = h2_mul(v | (v << 16), ftz_h2(Bm2[ci * P2 + j]));
+#pragma unroll
+        for (int i = 0; i < LAT; i++)
+            if (i == lane) part[i] = h2_add(part[i], prod);
+        lane = (lane + 1 == LAT) ? 0 : lane + 1;
+    }
+    unsigned acc = part[0];
+#pragma unroll
+    for (int i = 1; i < LAT; i++) acc = h2_add(acc, part[i]);
+    if (relu) {
+        // keep a half iff it is > 0 (not NaN, not negative, not zero)
+        const __half2 a2 = *reinterpret_cast<const __half2*>(&acc);
+        const bool lo = __half2float(__low2half(a2)) > 0.f, hi = __half2float(__high2half(a2)) > 0.f;
+        acc &= (lo ? 0xffffu : 0u) | (hi ? 0xffff0000u : 0u);
+    }
+    out2[(long long)r * P2 + j] = acc;
 }
 
 // ---------------------------------------------------------------------------------

@@ -113,4 +113,36 @@ __global__ void dense_fill_kernel(const float* __restrict__ X, int n, int m, con
 }
 
 }  // namespace prep
+
+// ---- adaptive pruning (sgrace.py:626-629): adjacency entries whose quantised code is 0 are dropped -------------
+// flag[k] = 1 iff clip(round(a_k / a_s + z), 0, 2^q - 1) != 0   (quantization_ufbits, round-half-even); flag[nnz] = 0
+__global__ void prune_flag_kernel(const float* __restrict__ val, long long nnz, float inv_as, int a_z, int qbits, int* __restrict__ flag) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > nnz) return;
+    int f = 0;
+    if (k < nnz) {
+        float r = rintf(__fadd_rn(__fmul_rn(inv_as, val[k]), (float)a_z));
+        const float hi = (float)((1 << qbits) - 1);
+        r = r < 0.f ? 0.f : (r > hi ? hi : r);
+        f = r != 0.f;
+    }
+    flag[k] = f;
+}
+// pos = exclusive prefix sum of flag (nnz + 1 entries): survivors keep their order
+__global__ void prune_scatter_kernel(const int* __restrict__ col, const float* __restrict__ val, const int* __restrict__ pos, long long nnz,
+                                     int* __restrict__ out_col, float* __restrict__ out_val, int* __restrict__ kept) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nnz) return;
+    const int p0 = pos[k];
+    if (pos[k + 1] != p0) {
+        out_col[p0] = col[k];
+        out_val[p0] = val[k];
+        if (kept) kept[p0] = (int)k;
+    }
+}
+__global__ void prune_rowptr_kernel(const int* __restrict__ rowptr, const int* __restrict__ pos, int n, int* __restrict__ out_rowptr) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r <= n) out_rowptr[r] = pos[rowptr[r]];
+}
+
 }  // namespace sgrace

@@ -106,3 +106,59 @@ def test_prepared_graph_feeds_the_layer():
     h.adj_run(d, xwd.data_ptr(), n)
     h.wait()
     U.assert_close_f32(out.cpu().numpy(), want, what="ADJ on the GPU-prepared graph")
+
+
+@pytest.mark.parametrize("qbits,gat", [(4, 0), (4, 1), (8, 1), (2, 0)])
+def test_prune_adjacency_compaction_keeps_the_layer_bit_for_bit(qbits, gat):
+    """Adaptive pruning made explicit (sgrace.py:626-629): dropping the zero-coded adjacency entries once leaves D
+    unchanged (GCN: bit for bit; GAT: to rounding, logits bit for bit through the `kept` map); the surviving set
+    equals the numpy restatement."""
+    import torch
+    from sgracex1_b200 import _lib, quant as Q
+    from sgracex1_b200.driver import DeviceLayer
+    from sgracex1_b200.pynq_compat import MmultTop
+    from sgracex1_b200 import graphs as G
+    p = G.pubmed_shape(seed=5)
+    rng = np.random.default_rng(3)
+    # a wide spread of edge weights so that a good share of them quantise to code 0
+    val = (p.adj_val * rng.choice([1.0, 0.3, 0.05, 0.01], size=len(p.adj_val))).astype(np.float32)
+    c = Q.layer_constants(qbits)
+    inv_as = np.float32(1.0 / c["a_s"])
+    codes = np.clip(np.rint(inv_as * val), 0, 2 ** qbits - 1)
+    keep = codes != 0
+    assert 0.05 < 1.0 - keep.mean() < 0.95
+    ip = MmultTop(0)
+    ip.configure(mode=_lib.MODE_FULL, qbits=qbits, staging=0, index_format=0)
+    dev = "cuda:0"
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
+    rp, ci, va = t(p.adj_rowptr, np.int32), t(p.adj_col, np.int32), t(val, np.float32)
+    nnz = len(val)
+    rp2, ci2, va2, kept = torch.zeros_like(rp), torch.zeros_like(ci), torch.zeros_like(va), torch.zeros_like(ci)
+    n2 = ip.handle.prune_adjacency(rp.data_ptr(), ci.data_ptr(), va.data_ptr(), p.N, nnz, float(inv_as), qbits,
+                                   rp2.data_ptr(), ci2.data_ptr(), va2.data_ptr(), kept.data_ptr())
+    assert n2 == int(keep.sum())
+    assert np.array_equal(kept[:n2].cpu().numpy(), np.nonzero(keep)[0])
+    assert np.array_equal(ci2[:n2].cpu().numpy(), p.adj_col[keep]) and np.array_equal(va2[:n2].cpu().numpy(), val[keep])
+    want_rp = np.concatenate([[0], np.cumsum(np.add.reduceat(keep.astype(np.int64), p.adj_rowptr[:-1]) *
+                                             (np.diff(p.adj_rowptr) > 0))]).astype(np.int32)
+    assert np.array_equal(rp2.cpu().numpy(), want_rp)
+    att = rng.uniform(-0.6, 0.6, size=2 * p.P).astype(np.float32)
+    outs = []
+    for adj in ((p.adj_rowptr, p.adj_col, val), (rp2.cpu().numpy(), ci2[:n2].cpu().numpy(), va2[:n2].cpu().numpy())):
+        dl = DeviceLayer(ip.handle, _lib.MODE_FULL, device=dev)
+        dl.load(N=p.N, M=p.M, P=p.P, adj=adj, fea=(p.fea_rowptr, p.fea_col, p.fea_val), B=p.B, relu=1, attention=att,
+                gat_mode=gat, consts=c, want_es=True)
+        dl.run()
+        outs.append((dl.result("D"), dl.result("E"), dl.result("S")))
+    (d0, e0, s0), (d1, e1, s1) = outs
+    if not gat:
+        # the GCN sum of a row runs over the survivors in their order either way: identical bits
+        assert np.array_equal(d0.view(np.uint32), d1.view(np.uint32))
+    else:
+        # the softmax sums are grouped by the position of an edge in its row, which compaction changes: the logits
+        # are identical, weights and output agree to rounding
+        k = np.nonzero(keep)[0]
+        assert np.array_equal(e0[k].view(np.uint32), e1[:n2].view(np.uint32))
+        np.testing.assert_allclose(s1[:n2], s0[k], rtol=2e-6, atol=1e-9)
+        U.assert_close_f32(d1, d0, rtol=2e-6, what="GAT on the compacted adjacency")
+        assert not e0[~keep].any() and not s0[~keep].any()
