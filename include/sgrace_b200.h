@@ -88,6 +88,16 @@ enum {
                                        launch (W transpose | FEA | ADJ with grid barriers); default 65536, 0 = off */
     SGRACE_OPT_ACCUMULATE = 17,     /* 1: the ADJ stage computes D = act(D + A.XW): the second pass over an
                                        adjacency split by column ownership (multi-GPU halo)  */
+    SGRACE_OPT_ADJ_PLAN = 20,       /* FAST-mode ADJ on block-diagonal adjacencies (batched graphs) with the XW window of a
+                                       panel of graphs in shared memory (csrc/sgrace_spmm_panel.cuh).  0 (default): off --
+                                       measured slower than the gather kernel when a graph's window leaves little room for
+                                       the CSR rings (Cora-size blocks: 0.23 ms against 0.17 ms);
+                                       1: the panel plan of an adjacency is found once per (rowPtr, columnIndex, sizes)
+                                       and reused; 2: re-analysed at every launch.  A stale plan only costs speed:
+                                       columns outside a panel's window are gathered from global memory, results are
+                                       bit-equal to the gather kernel                                                   */
+    SGRACE_OPT_PANEL_LAUNCHES = 21, /* read-only: launches of the panel kernel so far                                  */
+    SGRACE_OPT_PLAN_BUILDS = 22,    /* read-only: panel plans analysed so far                                          */
     SGRACE_OPT_AGG_FIRST = 16       /* 1: dense layers with M_fea < P_w run as act((A.X).W) --
                                        equal up to float rounding, gathers narrower rows;
                                        0 (default): the reference's order act(A.(X.W))      */

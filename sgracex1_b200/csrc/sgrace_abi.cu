@@ -9,8 +9,12 @@
 #include "sgrace_kernels.cuh"
 #include "sgrace_gemm_tc.cuh"
 #include "sgrace_spmm_stream.cuh"
+#include "sgrace_spmm_panel.cuh"
 #include "sgrace_prep.cuh"
 
+#include <cub/device/device_select.cuh>
+#include <cuda/functional>
+#include <thrust/iterator/counting_iterator.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
@@ -38,6 +42,19 @@ struct Scratch {
     size_t bytes = 0;
 };
 
+// Panel plan of one adjacency (sgrace_spmm_panel.cuh): found once per (arrays, sizes, window capacity) and reused
+struct AdjPlan {
+    const int* rp = nullptr;
+    const int* ci = nullptr;
+    int nrows = 0, cap_fit = 0;
+    long long nnz = 0;
+    int npanels = 0, windowed_rows = 0;
+    bool usable = false;
+    int4* panels = nullptr;     // device
+    int* info = nullptr;        // device: {npanels, windowed rows}
+    uint64_t last_use = 0;
+};
+
 }  // namespace
 
 struct sgrace_handle {
@@ -51,6 +68,10 @@ struct sgrace_handle {
     int mode = SGRACE_MODE_F32_FAST;
     int spmm_block = 1, lat_fea = 0, lat_adj = 0, fea_threads = 1, adj_threads = 1, use_sblocks = 0;
     int index_format = 0, qbits = 8, staging = 1, long_row = 512, validate = 0, dense_tc = 1, stream_kernel = 1, agg_first = 0, accumulate = 0;
+    int adj_plan = 0;                           // SGRACE_OPT_ADJ_PLAN (opt-in: measured slower than the gather kernel on Cora-size blocks)
+    std::vector<AdjPlan> plans;                 // small cache of panel plans
+    uint64_t plan_clock = 0, plan_builds = 0, panel_launches = 0;
+    Scratch plan_a, plan_b, plan_c, plan_d, plan_flag, plan_starts, plan_tmp;
     int row_offset = 0;                         // global index of the ADJ stage's local row 0 (row-partitioned GAT)
     int fused_small = 65536;                    // layers with at most this many rows run as one cooperative launch (0: off)
     unsigned counter_phase = 0;                 // which of the two counter sets the next SpMM launch uses
@@ -69,6 +90,7 @@ struct sgrace_handle {
     struct StreamTune {
         int c_s = 0, c_g = 0, g_s = 0, g_g = 0, s_s = 0, s_g = 0, tr_s = 0, tr_g = 0, threads_s = 0, threads_g = 0;
         int ctas = 0, nosmem = 0, long_noseg = 0, live = 0;
+        int p_c = 0, p_g = 0, p_s = 0, p_tr = 0, p_ncw = 0, p_long = 0, p_dbg = 0;      // panel kernel (SGRACE_PANEL_*)
     } tune;
     std::map<std::pair<const void*, uint64_t>, int> launch_cfg;   // (kernel, threads << 32 | smem) -> resident CTAs per SM
     int* max_fea_dev = nullptr;
@@ -140,6 +162,8 @@ void load_tune(sgrace_handle* h) {
     t.nosmem = env_int("SGRACE_STREAM_NOSMEM", 0);
     t.long_noseg = env_int("SGRACE_LONG_NOSEG", 0);
     t.live = env_int("SGRACE_TUNE_LIVE", 0);
+    t.p_c = env_int("SGRACE_PANEL_C", 0); t.p_g = env_int("SGRACE_PANEL_G", 0); t.p_s = env_int("SGRACE_PANEL_S", 0);
+    t.p_tr = env_int("SGRACE_PANEL_TR", 0); t.p_ncw = env_int("SGRACE_PANEL_NCW", 0); t.p_long = env_int("SGRACE_PANEL_LONG", 0); t.p_dbg = env_int("SGRACE_PANEL_DBG", 0);
 }
 
 // resident CTAs per SM of `kern` at this block size / dynamic shared memory; the attribute call and the occupancy
@@ -391,6 +415,150 @@ int launch_spmm_stream(sgrace_handle* h, const int* rp, const int* ci, const flo
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------
+// panel (shared-memory window) ADJ: plan + launch
+// ------------------------------------------------------------------------------------
+struct PanelGeom { int G, S, C, TR, ncw, threads, cap_fit, hub; size_t smem; int win_bytes; };
+
+// ring geometry of the panel kernel for rows of `rowbytes`; the window gets what the rings leave
+bool panel_geometry(const sgrace_handle* h, int rowbytes, double avg_nnz, PanelGeom* g) {
+    const auto& tn = h->tune;
+    if (avg_nnz < 1.0) avg_nnz = 1.0;
+    g->G = tn.p_g > 0 ? tn.p_g : 2;
+    g->S = tn.p_s > 0 ? tn.p_s : 3;
+    g->C = tn.p_c > 0 ? (tn.p_c & ~3) : 1024;
+    g->hub = tn.p_long > 0 ? tn.p_long : 32;
+    int TR = tn.p_tr > 0 ? tn.p_tr : (int)(1.25 * g->C / avg_nnz);
+    TR = (TR / 32) * 32;
+    if (TR < 64) TR = 64;
+    if (TR > 512) TR = 512;
+    g->TR = TR;
+    if (g->G < 1 || g->G > 8) return false;
+    g->ncw = tn.p_ncw > 0 ? tn.p_ncw : (23 / g->G) - 1;          // 768 threads: 85 registers each, no spills
+    if (g->ncw < 1) return false;
+    g->threads = 32 * (g->G * (1 + g->ncw) + 1);
+    if (g->threads > 768) return false;
+    const size_t fixed = panel_smem_bytes(g->G, g->S, g->TR, g->C, 0);
+    if (fixed + 16 * 1024 > (size_t)h->smem_optin) return false;
+    g->win_bytes = (int)(((size_t)h->smem_optin - fixed) & ~(size_t)127);
+    g->cap_fit = g->win_bytes / rowbytes;
+    g->smem = panel_smem_bytes(g->G, g->S, g->TR, g->C, g->win_bytes);
+    return g->cap_fit >= 64;
+}
+
+// finds (or builds) the plan of this adjacency; *out = nullptr when the panel kernel should not be used
+int adj_plan_for(sgrace_handle* h, const int* rp, const int* ci, int nrows, long long nnz, int cap_fit, const AdjPlan** out) {
+    *out = nullptr;
+    h->plan_clock++;
+    if (h->adj_plan != 2) {
+        for (auto& pl : h->plans)
+            if (pl.rp == rp && pl.ci == ci && pl.nrows == nrows && pl.nnz == nnz && pl.cap_fit == cap_fit) {
+                pl.last_use = h->plan_clock;
+                if (pl.usable) *out = &pl;
+                return 0;
+            }
+    }
+    // building needs a device->host read of two ints: not inside a stream capture
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    CU(cudaStreamIsCapturing(h->stream, &cap));
+    if (cap != cudaStreamCaptureStatusNone) return 0;
+    AdjPlan* slot = nullptr;
+    for (auto& pl : h->plans)
+        if (pl.rp == rp && pl.ci == ci && pl.nrows == nrows && pl.nnz == nnz && pl.cap_fit == cap_fit) slot = &pl;
+    if (!slot) {
+        if (h->plans.size() < 8) { h->plans.emplace_back(); slot = &h->plans.back(); }
+        else { slot = &h->plans[0]; for (auto& pl : h->plans) if (pl.last_use < slot->last_use) slot = &pl; }
+    }
+    CU(cudaStreamSynchronize(h->stream));           // a plan that is being replaced may still be in use
+    if (slot->panels) { cudaFree(slot->panels); slot->panels = nullptr; }
+    if (!slot->info) CU(cudaMalloc(&slot->info, 16));
+    const size_t n = (size_t)nrows;
+    if (int rc = ensure(h, h->plan_a, 4 * n)) return rc;
+    if (int rc = ensure(h, h->plan_b, 4 * n)) return rc;
+    if (int rc = ensure(h, h->plan_c, 4 * n)) return rc;
+    if (int rc = ensure(h, h->plan_d, 4 * n)) return rc;
+    if (int rc = ensure(h, h->plan_flag, n)) return rc;
+    if (int rc = ensure(h, h->plan_starts, 4 * n + 16)) return rc;
+    int *hi = (int*)h->plan_a.p, *lo_rev = (int*)h->plan_b.p, *pmax = (int*)h->plan_c.p, *smin = (int*)h->plan_d.p;
+    unsigned char* flag = (unsigned char*)h->plan_flag.p;
+    int* starts = (int*)h->plan_starts.p;
+    int* nstarts = starts + n;
+    const int blocks = (nrows + 255) / 256;
+    plan::row_extent_kernel<<<blocks, 256, 0, h->stream>>>(rp, ci, nrows, hi, lo_rev);
+    size_t t1 = 0, t2 = 0, t3 = 0;
+    CU(cub::DeviceScan::InclusiveScan(nullptr, t1, hi, pmax, cuda::maximum<>{}, nrows, h->stream));
+    CU(cub::DeviceScan::InclusiveScan(nullptr, t2, lo_rev, smin, cuda::minimum<>{}, nrows, h->stream));
+    thrust::counting_iterator<int> counting(0);
+    CU(cub::DeviceSelect::Flagged(nullptr, t3, counting, flag, starts, nstarts, nrows, h->stream));
+    size_t tmp = t1 > t2 ? t1 : t2; if (t3 > tmp) tmp = t3;
+    if (int rc = ensure(h, h->plan_tmp, tmp + 16)) return rc;
+    CU(cub::DeviceScan::InclusiveScan(h->plan_tmp.p, t1, hi, pmax, cuda::maximum<>{}, nrows, h->stream));
+    CU(cub::DeviceScan::InclusiveScan(h->plan_tmp.p, t2, lo_rev, smin, cuda::minimum<>{}, nrows, h->stream));
+    plan::block_flag_kernel<<<blocks, 256, 0, h->stream>>>(pmax, smin, nrows, flag);
+    CU(cub::DeviceSelect::Flagged(h->plan_tmp.p, t3, counting, flag, starts, nstarts, nrows, h->stream));
+    // panels of a few per SM when the graph is small, never more rows than the window holds
+    int cap_pack = (int)((long long)nrows / ((long long)h->num_sms * 4) + 1);
+    if (cap_pack < 256) cap_pack = 256;
+    if (cap_pack > cap_fit) cap_pack = cap_fit;
+    int nstarts_h = 0;
+    CU(cudaMemcpyAsync(&nstarts_h, nstarts, 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    const size_t max_panels = (size_t)nstarts_h + n / cap_pack + 2;
+    CU(cudaMalloc(&slot->panels, sizeof(int4) * max_panels));
+    plan::pack_kernel<<<1, 1024, 0, h->stream>>>(starts, nstarts, nrows, cap_fit, cap_pack, slot->panels, slot->info);
+    h->launches += 6;
+    CU(cudaGetLastError());
+    int info_h[2] = {0, 0};
+    CU(cudaMemcpyAsync(info_h, slot->info, 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    slot->rp = rp; slot->ci = ci; slot->nrows = nrows; slot->nnz = nnz; slot->cap_fit = cap_fit;
+    slot->npanels = info_h[0]; slot->windowed_rows = info_h[1];
+    // worth it when most rows get a window and there is a panel for every SM
+    slot->usable = info_h[0] >= h->num_sms && (double)info_h[1] >= 0.9 * (double)nrows;
+    slot->last_use = h->plan_clock;
+    h->plan_builds++;
+    if (slot->usable) *out = slot;
+    return 0;
+}
+
+// returns -100 when the panel kernel does not apply (the caller takes the gather kernel)
+template <int LPR, int NV>
+int launch_spmm_panel(sgrace_handle* h, const int* rp, const int* ci, const float* va, const float* Bm, float* out,
+                      int nrows, int P, int relu, long long nnz_hint, int final_out, int b_total_rows) {
+    if (NV > 2) return -100;
+    const int rowbytes = P * 4;
+    PanelGeom g;
+    if (h->tune.live) load_tune(h);
+    if (!panel_geometry(h, rowbytes, nrows > 0 ? (double)nnz_hint / nrows : 8.0, &g)) return -100;
+    const AdjPlan* pl = nullptr;
+    if (int rc = adj_plan_for(h, rp, ci, nrows, nnz_hint, g.cap_fit, &pl)) return rc;
+    if (!pl) return -100;
+    if (int rc = ensure(h, h->lists, sizeof(int) * (size_t)(nrows > 0 ? nrows : 1))) return rc;
+    int *cset, *nset;
+    if (int rc = counter_sets(h, &cset, &nset)) return rc;
+    PanelParams pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.rowptr = rp; pp.col = ci; pp.val = va; pp.Bm = (const float4*)Bm; pp.out = (float4*)out;
+    pp.nrows = nrows; pp.relu = relu; pp.streaming_store = final_out; pp.bm_rows = b_total_rows;
+    pp.long_thresh = h->long_row; pp.hub_thresh = g.hub < h->long_row ? g.hub : h->long_row;
+    pp.tile_rows = g.TR; pp.stage_nnz = g.C; pp.stages = g.S; pp.groups = g.G;
+    pp.win_bytes = g.win_bytes; pp.panels = pl->panels; pp.npanels = pl->info;
+    pp.long_rows = (int*)h->lists.p; pp.long_count = cset; pp.panel_counter = cset + 3;
+    pp.dbg = h->tune.p_dbg;
+    auto kern = spmm_panel_f32_kernel<LPR, NV, 768>;
+    int per_sm = 0;
+    if (int rc = launch_config(h, kern, g.threads, g.smem, &per_sm)) return rc;
+    if (per_sm < 1) return fail(h, SGRACE_ECUDA, "panel SpMM does not fit an SM (%zu B smem)", g.smem);
+    int grid = h->num_sms < pl->npanels ? h->num_sms : pl->npanels;
+    kern<<<grid, g.threads, g.smem, h->stream>>>(pp);
+    h->launches++;
+    h->panel_launches++;
+    CU(cudaGetLastError());
+    constexpr int NVL = (LPR * NV + 31) / 32 > 0 ? (LPR * NV + 31) / 32 : 1;
+    return launch_long_rows<NVL>(h, rp, ci, va, Bm, out, P / 4, relu, pp.long_rows, pp.long_count, nnz_hint, nset);
+}
+
 template <int NC>
 int launch_spmm_scalar(sgrace_handle* h, const int* rp, const int* ci, const float* va, const float* Bm,
                        float* out, int nrows, int P, int relu) {
@@ -408,6 +576,18 @@ int spmm_f32(sgrace_handle* h, const int* rp, const int* ci, const float* va, co
     const bool aligned = (P % 4 == 0) && (((uintptr_t)Bm & 15) == 0) && (((uintptr_t)out & 15) == 0);
     // the streaming kernel bulk-copies 16-byte groups of the CSR arrays
     const bool csr_aligned = ((((uintptr_t)rp) | ((uintptr_t)ci) | ((uintptr_t)va)) & 15) == 0;
+    if (aligned && csr_aligned && h->stream_kernel && h->adj_plan && b_rows == 0 && b_total_rows == nrows && nnz_hint > 0 &&
+        !h->accumulate && h->peer_count == 0 && nrows >= 4096) {
+        // square adjacency: try the shared-memory window kernel (block-diagonal batches); -100 = does not apply
+        const int P4 = P / 4;
+        int rc = -100;
+#define SGRACE_PANEL(L, V) rc = launch_spmm_panel<L, V>(h, rp, ci, va, Bm, out, nrows, P, relu, nnz_hint, final_out, b_total_rows)
+        if (P4 == 1) SGRACE_PANEL(1, 1); else if (P4 == 2) SGRACE_PANEL(2, 1); else if (P4 == 4) SGRACE_PANEL(4, 1);
+        else if (P4 == 8) SGRACE_PANEL(8, 1); else if (P4 == 16) SGRACE_PANEL(16, 1); else if (P4 == 32) SGRACE_PANEL(32, 1);
+        else if (P4 == 64) SGRACE_PANEL(32, 2);
+#undef SGRACE_PANEL
+        if (rc != -100) return rc;
+    }
     if (aligned && csr_aligned && h->stream_kernel) {
         const int P4 = P / 4;
 #define SGRACE_STREAM(L, V) return launch_spmm_stream<L, V>(h, rp, ci, va, Bm, out, nrows, P, relu, nnz_hint, b_rows, final_out, b_total_rows)
@@ -1032,7 +1212,8 @@ int sgrace_destroy(sgrace_handle* h) {
         cudaFree(kv.second.dev);
         cudaFreeHost(kv.second.host);
     }
-    Scratch* all[] = {&h->wrm, &h->ax, &h->long_partial, &h->long_done, &h->xw, &h->wq, &h->s1, &h->s2, &h->rp_fea, &h->rp_adj, &h->lists, &h->counters, &h->prep_keys, &h->prep_ids, &h->prep_misc, &h->prep_tmp};
+    for (auto& pl : h->plans) { if (pl.panels) cudaFree(pl.panels); if (pl.info) cudaFree(pl.info); }
+    Scratch* all[] = {&h->plan_a, &h->plan_b, &h->plan_c, &h->plan_d, &h->plan_flag, &h->plan_starts, &h->plan_tmp, &h->wrm, &h->ax, &h->long_partial, &h->long_done, &h->xw, &h->wq, &h->s1, &h->s2, &h->rp_fea, &h->rp_adj, &h->lists, &h->counters, &h->prep_keys, &h->prep_ids, &h->prep_misc, &h->prep_tmp};
     for (Scratch* s : all) if (s->p) cudaFree(s->p);
     if (h->max_fea_dev) cudaFree(h->max_fea_dev);
     for (int i = 0; i < 5; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -1148,6 +1329,7 @@ int sgrace_set_option(sgrace_handle* h, int key, int64_t v) {
         case SGRACE_OPT_ACCUMULATE: h->accumulate = v != 0; break;
         case SGRACE_OPT_FUSED_SMALL: if (v < 0) return fail(h, SGRACE_EINVAL, "fused_small < 0"); h->fused_small = (int)v; break;
         case SGRACE_OPT_ROW_OFFSET: if (v < 0) return fail(h, SGRACE_EINVAL, "row_offset < 0"); h->row_offset = (int)v; break;
+        case SGRACE_OPT_ADJ_PLAN: if (v < 0 || v > 2) return fail(h, SGRACE_EINVAL, "adj_plan must be 0,1,2"); h->adj_plan = (int)v; break;
         default: return fail(h, SGRACE_EINVAL, "unknown option %d", key);
     }
     return SGRACE_OK;
@@ -1175,6 +1357,9 @@ int sgrace_get_option(sgrace_handle* h, int key, int64_t* v) {
         case SGRACE_OPT_ACCUMULATE: *v = h->accumulate; break;
         case SGRACE_OPT_FUSED_SMALL: *v = h->fused_small; break;
         case SGRACE_OPT_ROW_OFFSET: *v = h->row_offset; break;
+        case SGRACE_OPT_ADJ_PLAN: *v = h->adj_plan; break;
+        case SGRACE_OPT_PANEL_LAUNCHES: *v = (int64_t)h->panel_launches; break;
+        case SGRACE_OPT_PLAN_BUILDS: *v = (int64_t)h->plan_builds; break;
         default: return fail(h, SGRACE_EINVAL, "unknown option %d", key);
     }
     return SGRACE_OK;
