@@ -68,6 +68,10 @@ struct sgrace_handle {
     int mode = SGRACE_MODE_F32_FAST;
     int spmm_block = 1, lat_fea = 0, lat_adj = 0, fea_threads = 1, adj_threads = 1, use_sblocks = 0;
     int index_format = 0, qbits = 8, staging = 1, long_row = 512, validate = 0, dense_tc = 1, stream_kernel = 1, agg_first = 0, accumulate = 0;
+    int overlap = 1;                            // SGRACE_OPT_OVERLAP
+    cudaStream_t s_up = nullptr, s_down = nullptr;   // staging copies beside the kernels (created on first use)
+    std::vector<cudaEvent_t> ev_pool;
+    uint64_t overlapped_starts = 0;
     int adj_plan = 0;                           // SGRACE_OPT_ADJ_PLAN (opt-in: measured slower than the gather kernel on Cora-size blocks)
     std::vector<AdjPlan> plans;                 // small cache of panel plans
     uint64_t plan_clock = 0, plan_builds = 0, panel_launches = 0;
@@ -1135,24 +1139,111 @@ const Buffer* find_buffer(const sgrace_handle* h, uint64_t a, size_t* offset) {
     return nullptr;
 }
 
-int stage_in(sgrace_handle* h, uint64_t addr, size_t bytes) {
+// host mirror -> device for bytes [skip, skip + bytes) behind device address addr, on stream st (0: the handle's)
+int stage_in(sgrace_handle* h, uint64_t addr, size_t bytes, size_t skip = 0, cudaStream_t st = nullptr) {
     size_t off;
     const Buffer* b = find_buffer(h, addr, &off);
     if (!b || bytes == 0) return 0;
-    if (off + bytes > b->bytes)
-        return fail(h, SGRACE_EBOUNDS, "layer needs %zu bytes at buffer offset %zu but the allocation has %zu", bytes,
+    if (off + skip + bytes > b->bytes)
+        return fail(h, SGRACE_EBOUNDS, "layer needs %zu bytes at buffer offset %zu but the allocation has %zu", skip + bytes,
                     off, b->bytes);
-    CU(cudaMemcpyAsync((char*)b->dev + off, (char*)b->host + off, bytes, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync((char*)b->dev + off + skip, (char*)b->host + off + skip, bytes, cudaMemcpyHostToDevice, st ? st : h->stream));
     return 0;
 }
-int stage_out(sgrace_handle* h, uint64_t addr, size_t bytes) {
+int stage_out(sgrace_handle* h, uint64_t addr, size_t bytes, size_t skip = 0, cudaStream_t st = nullptr) {
     size_t off;
     const Buffer* b = find_buffer(h, addr, &off);
     if (!b || bytes == 0) return 0;
-    if (off + bytes > b->bytes)
-        return fail(h, SGRACE_EBOUNDS, "layer writes %zu bytes at buffer offset %zu but the allocation has %zu", bytes,
+    if (off + skip + bytes > b->bytes)
+        return fail(h, SGRACE_EBOUNDS, "layer writes %zu bytes at buffer offset %zu but the allocation has %zu", skip + bytes,
                     off, b->bytes);
-    CU(cudaMemcpyAsync((char*)b->host + off, (char*)b->dev + off, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync((char*)b->host + off + skip, (char*)b->dev + off + skip, bytes, cudaMemcpyDeviceToHost, st ? st : h->stream));
+    return 0;
+}
+
+// Large float32 layers with host buffers: the copies run beside the kernels.  The feature operand and B go up on the
+// handle's stream and the feature stage starts behind them; the adjacency goes up in row panels on a second stream,
+// the aggregation runs panel by panel as the slices land, and each panel of D goes down on a third stream while the
+// next panel's slices are still going up (host->device and device->host use different copy engines).
+// Returns -100 when the layer does not qualify (the caller takes the serial path).
+int start_overlapped(sgrace_handle* h, sgrace_layer_desc& d, uint64_t a_rpf, uint64_t a_cif, uint64_t a_vf, uint64_t a_rpa,
+                     uint64_t a_cia, uint64_t a_va, uint64_t a_b, uint64_t a_d, long long nnz_fea, long long nnz_adj) {
+    const size_t N = (size_t)d.N_adj, M = (size_t)d.M_fea, P = (size_t)d.P_w;
+    if (!h->overlap || h->mode != SGRACE_MODE_F32_FAST || h->index_format != 0 || h->agg_first || h->accumulate ||
+        h->peer_count > 0 || d.gemm_mode == 2 || d.gat_mode)
+        return -100;
+    const size_t d_bytes = N * P * 4;
+    if (d_bytes < ((size_t)16 << 20) || (h->fused_small && d.N_adj <= h->fused_small)) return -100;
+    size_t off_rp;
+    const Buffer* brp = find_buffer(h, a_rpa, &off_rp);
+    if (!brp || !find_buffer(h, a_cia, &off_rp) || !find_buffer(h, a_va, &off_rp) || !find_buffer(h, a_d, &off_rp)) return -100;
+    const Buffer* b0 = find_buffer(h, a_rpa, &off_rp);
+    const int* rp_host = (const int*)((const char*)b0->host + off_rp);
+    if (rp_host[0] != 0) return -100;
+    // panels of D of about 24 MB, row counts a multiple of 128 (the row-pointer slice of a panel stays 16-byte aligned)
+    int K = (int)((d_bytes + ((size_t)24 << 20) - 1) / ((size_t)24 << 20));
+    if (K < 2) K = 2;
+    if (K > 16) K = 16;
+    size_t rows_per = ((N + K - 1) / K + 127) & ~(size_t)127;
+    K = (int)((N + rows_per - 1) / rows_per);
+    if (K < 2) return -100;
+    if (!h->s_up) CU(cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking));
+    if (!h->s_down) CU(cudaStreamCreateWithFlags(&h->s_down, cudaStreamNonBlocking));
+    while ((int)h->ev_pool.size() < 2 * K + 3) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->ev_pool.push_back(e);
+    }
+    cudaEvent_t ev_prev = h->ev_pool[2 * K], ev_fup = h->ev_pool[2 * K + 1], ev_down = h->ev_pool[2 * K + 2];
+    // whatever was queued on the handle's stream before this start comes first on the side streams too
+    CU(cudaEventRecord(ev_prev, h->stream));
+    CU(cudaStreamWaitEvent(h->s_up, ev_prev, 0));
+    CU(cudaStreamWaitEvent(h->s_down, ev_prev, 0));
+    // feature operand + B on the handle's stream, then the feature stage
+    if (d.gemm_mode == 0) {
+        if (int rc = stage_in(h, a_rpf, (N + 1) * 4)) return rc;
+        if (int rc = stage_in(h, a_cif, (size_t)nnz_fea * 4)) return rc;
+        if (int rc = stage_in(h, a_vf, (size_t)nnz_fea * 4)) return rc;
+    } else {
+        if (int rc = stage_in(h, a_vf, N * M * 4)) return rc;
+    }
+    if (int rc = stage_in(h, a_b, M * P * 4)) return rc;
+    CU(cudaEventRecord(ev_fup, h->stream));
+    // adjacency: the row pointers at once, then (column, value) slices panel by panel, behind the feature upload so
+    // that the feature stage is not delayed
+    CU(cudaStreamWaitEvent(h->s_up, ev_fup, 0));
+    if (int rc = stage_in(h, a_rpa, (N + 1) * 4, 0, h->s_up)) return rc;
+    for (int i = 0; i < K; i++) {
+        const size_t r0 = (size_t)i * rows_per, r1 = r0 + rows_per < N ? r0 + rows_per : N;
+        const long long k0 = rp_host[r0], k1 = rp_host[r1];
+        if (k0 < 0 || k1 < k0 || k1 > nnz_adj) return fail(h, SGRACE_EBOUNDS, "adjacency row pointers not monotonic around row %zu", r0);
+        if (int rc = stage_in(h, a_cia, (size_t)(k1 - k0) * 4, (size_t)k0 * 4, h->s_up)) return rc;
+        if (int rc = stage_in(h, a_va, (size_t)(k1 - k0) * 4, (size_t)k0 * 4, h->s_up)) return rc;
+        CU(cudaEventRecord(h->ev_pool[i], h->s_up));
+    }
+    void* XW = d.XW;
+    if (!XW) {
+        if (int rc = ensure(h, h->xw, 4 * N * P + 16)) return rc;
+        XW = h->xw.p;
+    }
+    h->ev_valid = false;
+    CU(cudaEventRecord(h->ev[0], h->stream));
+    if (int rc = run_fea(h, &d, d.rowPtr_fea, XW)) return rc;
+    CU(cudaEventRecord(h->ev[1], h->stream));
+    for (int i = 0; i < K; i++) {
+        const size_t r0 = (size_t)i * rows_per, r1 = r0 + rows_per < N ? r0 + rows_per : N;
+        const long long k0 = rp_host[r0], k1 = rp_host[r1];
+        CU(cudaStreamWaitEvent(h->stream, h->ev_pool[i], 0));
+        if (int rc = spmm_f32(h, d.rowPtr_adj + r0, d.columnIndex_adj, (const float*)d.values_adj, (const float*)XW,
+                              (float*)d.D + r0 * P, (int)(r1 - r0), (int)P, d.relu != 0, k1 - k0, 0, 1, 0)) return rc;
+        CU(cudaEventRecord(h->ev_pool[K + i], h->stream));
+        CU(cudaStreamWaitEvent(h->s_down, h->ev_pool[K + i], 0));
+        if (int rc = stage_out(h, a_d, (r1 - r0) * P * 4, r0 * P * 4, h->s_down)) return rc;
+    }
+    CU(cudaEventRecord(h->ev[2], h->stream));
+    CU(cudaEventRecord(ev_down, h->s_down));
+    CU(cudaStreamWaitEvent(h->stream, ev_down, 0));     // the handle's stream ends when the last panel of D is on the host
+    h->overlapped_starts++;
     return 0;
 }
 const void* host_view(const sgrace_handle* h, uint64_t addr) {
@@ -1213,6 +1304,9 @@ int sgrace_destroy(sgrace_handle* h) {
         cudaFreeHost(kv.second.host);
     }
     for (auto& pl : h->plans) { if (pl.panels) cudaFree(pl.panels); if (pl.info) cudaFree(pl.info); }
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    if (h->s_up) { cudaStreamSynchronize(h->s_up); cudaStreamDestroy(h->s_up); }
+    if (h->s_down) { cudaStreamSynchronize(h->s_down); cudaStreamDestroy(h->s_down); }
     Scratch* all[] = {&h->plan_a, &h->plan_b, &h->plan_c, &h->plan_d, &h->plan_flag, &h->plan_starts, &h->plan_tmp, &h->wrm, &h->ax, &h->long_partial, &h->long_done, &h->xw, &h->wq, &h->s1, &h->s2, &h->rp_fea, &h->rp_adj, &h->lists, &h->counters, &h->prep_keys, &h->prep_ids, &h->prep_misc, &h->prep_tmp};
     for (Scratch* s : all) if (s->p) cudaFree(s->p);
     if (h->max_fea_dev) cudaFree(h->max_fea_dev);
@@ -1330,6 +1424,7 @@ int sgrace_set_option(sgrace_handle* h, int key, int64_t v) {
         case SGRACE_OPT_FUSED_SMALL: if (v < 0) return fail(h, SGRACE_EINVAL, "fused_small < 0"); h->fused_small = (int)v; break;
         case SGRACE_OPT_ROW_OFFSET: if (v < 0) return fail(h, SGRACE_EINVAL, "row_offset < 0"); h->row_offset = (int)v; break;
         case SGRACE_OPT_ADJ_PLAN: if (v < 0 || v > 2) return fail(h, SGRACE_EINVAL, "adj_plan must be 0,1,2"); h->adj_plan = (int)v; break;
+        case SGRACE_OPT_OVERLAP: h->overlap = v != 0; break;
         default: return fail(h, SGRACE_EINVAL, "unknown option %d", key);
     }
     return SGRACE_OK;
@@ -1358,6 +1453,8 @@ int sgrace_get_option(sgrace_handle* h, int key, int64_t* v) {
         case SGRACE_OPT_FUSED_SMALL: *v = h->fused_small; break;
         case SGRACE_OPT_ROW_OFFSET: *v = h->row_offset; break;
         case SGRACE_OPT_ADJ_PLAN: *v = h->adj_plan; break;
+        case SGRACE_OPT_OVERLAP: *v = h->overlap; break;
+        case SGRACE_OPT_OVERLAPPED_STARTS: *v = (int64_t)h->overlapped_starts; break;
         case SGRACE_OPT_PANEL_LAUNCHES: *v = (int64_t)h->panel_launches; break;
         case SGRACE_OPT_PLAN_BUILDS: *v = (int64_t)h->plan_builds; break;
         default: return fail(h, SGRACE_EINVAL, "unknown option %d", key);
@@ -1734,6 +1831,20 @@ int sgrace_start(sgrace_handle* h) {
     }
 
     CU(cudaEventRecord(h->ev[4], h->stream));
+    if (h->staging && !(full && h->qbits > 0)) {
+        const int rc = start_overlapped(h, d, a_rpf, a_cif, a_vf, a_rpa, a_cia, a_va, a_b, a_d, nnz_fea, nnz_adj);
+        if (rc != -100) {
+            if (rc) return rc;
+            const uint64_t a_prof = reg64(h, SGRACE_REG_PROFILING);
+            size_t off;
+            const Buffer* pb = find_buffer(h, a_prof, &off);
+            if (pb && off + 15 * 8 <= pb->bytes) memset((char*)pb->host + off, 0, 15 * 8);
+            CU(cudaEventRecord(h->ev[3], h->stream));
+            h->ev_valid = true;
+            h->running = true;
+            return SGRACE_OK;
+        }
+    }
     if (h->staging) {
         // host mirror -> device, only the ranges this layer reads
         const size_t rp_bytes_a = h->index_format == 0 ? (N + 1) * 4 : (size_t)nnz_adj * 4;

@@ -132,7 +132,7 @@ class MmultTop:
                     index_format=_lib.OPT_INDEX_FORMAT, qbits=_lib.OPT_QBITS, staging=_lib.OPT_STAGING,
                     long_row=_lib.OPT_LONG_ROW, validate=_lib.OPT_VALIDATE, dense_tc=_lib.OPT_DENSE_TC,
                     stream_kernel=_lib.OPT_STREAM_KERNEL, agg_first=_lib.OPT_AGG_FIRST,
-                    fused_small=_lib.OPT_FUSED_SMALL, row_offset=_lib.OPT_ROW_OFFSET, adj_plan=_lib.OPT_ADJ_PLAN)
+                    fused_small=_lib.OPT_FUSED_SMALL, row_offset=_lib.OPT_ROW_OFFSET, adj_plan=_lib.OPT_ADJ_PLAN, overlap=_lib.OPT_OVERLAP)
         for k, v in kw.items():
             if k == "leaky_alpha":
                 bits = int(np.asarray(v, dtype=np.float32).view(np.uint32))

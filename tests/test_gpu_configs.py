@@ -86,3 +86,38 @@ def test_benchmark_scale_properties(ip):
                   fea=(p0.fea_rowptr, p0.fea_col, p0.fea_val), B=p0.B, relu=1)
     U.assert_close_f32(D[:n], ref, what="first graph of the batch")
     ip.configure(staging=1)
+
+
+@pytest.mark.parametrize("dense", [False, True])
+def test_overlapped_staging_equals_the_serial_path(ip, dense):
+    """sgrace_start with host buffers on a layer whose D exceeds 16 MB: the adjacency upload in row panels, the
+    panel-by-panel aggregation and the panelled download of D (SGRACE_OPT_OVERLAP) give the bits of the serial path,
+    twice in a row (buffers and events are reused)."""
+    from sgracex1_b200.driver import HostLayer
+    probs = [G.cora_shape(seed=s, n=2708, m=96, nnz_fea=9000) for s in range(3)]
+    b = G.block_diagonal(probs, 120)
+    assert b.N * b.P * 4 >= 16 << 20
+    adj, fea = (b.adj_rowptr, b.adj_col, b.adj_val), (b.fea_rowptr, b.fea_col, b.fea_val)
+    rng = np.random.default_rng(3)
+    xd = rng.standard_normal((b.N, 8)).astype(np.float32) if dense else None
+    M = 8 if dense else b.M
+    B = (rng.uniform(-0.3, 0.3, size=(b.P, 8)).astype(np.float32).reshape(-1)) if dense else b.B
+    hl = HostLayer(ip, _lib.MODE_F32_FAST, N=b.N, M=M, P=b.P, nnz_adj=b.nnz_adj, nnz_fea=0 if dense else b.nnz_fea, dense=dense)
+    outs = []
+    for overlap in (0, 1, 1):
+        ip.configure(mode=_lib.MODE_F32_FAST, staging=1, index_format=0, overlap=overlap)
+        before = ip.handle.get_option(_lib.OPT_OVERLAPPED_STARTS)
+        if dense:
+            hl.load(N=b.N, M=M, P=b.P, adj=adj, x_dense=xd, B=B, relu=1)
+        else:
+            hl.load(N=b.N, M=M, P=b.P, adj=adj, fea=fea, B=B, relu=1)
+        hl.D[:] = -3.0
+        outs.append(hl.run().copy())
+        assert ip.handle.get_option(_lib.OPT_OVERLAPPED_STARTS) - before == overlap
+    hl.free()
+    ip.configure(overlap=1)
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    if not dense:
+        rows = np.r_[0:300, b.N - 300:b.N]
+        ref = O.layer(dtype=O.F32, N=b.N, M_fea=M, P=b.P, adj=adj, fea=fea, B=B, relu=1)
+        U.assert_close_f32(outs[1][rows], ref[rows], what="overlapped staging")
