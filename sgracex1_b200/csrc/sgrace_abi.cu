@@ -1714,6 +1714,14 @@ int sgrace_start(sgrace_handle* h) {
     if ((int32_t)h->regs[SGRACE_REG_BIAS_COUNT / 4] > 0) { h->running = true; h->ev_valid = false;
         CU(cudaEventRecord(h->ev[3], h->stream)); return SGRACE_OK; }
 
+    // layer_count > 1 / stream_mode != 0 (demo/emulation/config.py:6,17, sgrace.py:1862): several layers per start with
+    // the activations kept inside the device.  Every shipped configuration programs 1 / 0, and the open sources do not
+    // say where the closed design takes the next layer's weights and sizes from: refused rather than guessed.
+    if ((int32_t)h->regs[SGRACE_REG_LAYER_COUNT / 4] > 1 || (h->regs[SGRACE_REG_STREAM_MODE / 4] & 1u))
+        return fail(h, SGRACE_EUNSUPPORTED, "layer_count=%d stream_mode=%u: multi-layer streaming of the closed design is "
+                    "not specified by the open sources (config.py:6,17); program layer_count=1, stream_mode=0",
+                    (int)h->regs[SGRACE_REG_LAYER_COUNT / 4], h->regs[SGRACE_REG_STREAM_MODE / 4] & 1u);
+
     sgrace_layer_desc d;
     memset(&d, 0, sizeof(d));
     d.gemm_mode = (int32_t)h->regs[SGRACE_REG_GEMM_MODE / 4];

@@ -321,7 +321,7 @@ class HaloLayer:
         self.copy_lanes = [(self.hh, self.s_halo, None)]
         if exchange != "defer" and world > 1:
             from . import _lib
-            for _ in range(3):
+            for _ in range(min(6, world - 2)):   # up to one copy stream per destination
                 hx, sx = _lib.Handle(device.index or 0), torch.cuda.Stream(device)
                 hx.set_option(_lib.OPT_STAGING, 0)
                 hx.set_stream(sx.cuda_stream)

@@ -315,6 +315,10 @@ def test_errors_are_reported(ip):
         with pytest.raises(_lib.SgraceError):
             ip.register_map.CTRL.AP_START = 1
         ip.register_map.gemm_mode = 0
+        ip.register_map.layer_count = 2              # multi-layer streaming of the closed design: unspecified, refused
+        with pytest.raises(_lib.SgraceError, match="layer_count"):
+            ip.register_map.CTRL.AP_START = 1
+        ip.register_map.layer_count = 1
         ip.register_map.N_adj = 10_000_000           # larger than the allocation
         with pytest.raises(_lib.SgraceError):
             ip.register_map.CTRL.AP_START = 1
