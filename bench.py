@@ -286,7 +286,7 @@ def quantised_records(ip, local, hbm_peak, copies=32):
     return out
 
 
-def csim_record(ip, local, probs, hbm_peak, copies=64):
+def csim_record(ip, local, probs, hbm_peak, copies=256):
     """The mode the drop-in notebook runs in (binary16 buffers, C-simulation accumulate order, bit-exact):
     Cora-shape x`copies`, device-resident stage times."""
     from sgracex1_b200 import _lib, graphs as G

@@ -675,8 +675,13 @@ int stage_exact_any(sgrace_handle* h, int mode, int lat, const int* rp, const in
                 const long long items = (long long)nrows * (P / 2);
                 const long long g = (items + 255) / 256;
                 if (g > 0x7fffffffLL) return fail(h, SGRACE_EUNSUPPORTED, "problem too large for exact kernel");
-#define LAUNCH_X2(L) stage_exact_f16x2_kernel<L><<<(int)g, 256, 0, h->stream>>>(rp, ci, (const unsigned short*)va, (const unsigned*)Bm, \
-                                                                                 (unsigned*)out, nrows, P / 2, hw_threads, sblock, dense_M, relu)
+#define LAUNCH_X2(L)                                                                                                          \
+    do {                                                                                                                      \
+        if (dense_M > 0) stage_exact_f16x2_kernel<L, true><<<(int)g, 256, 0, h->stream>>>(rp, ci, (const unsigned short*)va, (const unsigned*)Bm, \
+                                                                                          (unsigned*)out, nrows, P / 2, hw_threads, sblock, dense_M, relu); \
+        else stage_exact_f16x2_kernel<L, false><<<(int)g, 256, 0, h->stream>>>(rp, ci, (const unsigned short*)va, (const unsigned*)Bm, \
+                                                                               (unsigned*)out, nrows, P / 2, hw_threads, sblock, dense_M, relu); \
+    } while (0)
                 switch (lat) {
                     case 1: LAUNCH_X2(1); break; case 2: LAUNCH_X2(2); break; case 3: LAUNCH_X2(3); break; case 4: LAUNCH_X2(4); break;
                     case 5: LAUNCH_X2(5); break; case 6: LAUNCH_X2(6); break; case 7: LAUNCH_X2(7); break; default: LAUNCH_X2(8); break;

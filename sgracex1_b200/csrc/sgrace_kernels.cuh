@@ -11,6 +11,7 @@
 // reshaped into a GEMM.  The one real contraction (dense FEA with a wide hidden layer)
 // lives in sgrace_gemm_tc.cuh.
 #pragma once
+#include <type_traits>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -893,15 +894,31 @@ stage_exact_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
 #pragma unroll
     for (int i = 0; i < LAT; i++) part[i] = Ops::zero();
     int lane = (beg - base) < 0x7fffffffLL ? (int)((unsigned)(beg - base) % (unsigned)LAT) : (int)((beg - base) % LAT);
-    for (long long k = beg; k < end; k++) {
-        const T v = val[k];
+    // partial sum `l` takes stream positions l, l + LAT, ... of the sblock (K:2009-2061).  Head: up to LAT - 1 entries
+    // until the position is a multiple of LAT (the only part that needs a run-time lane); body: LAT entries per trip,
+    // entry i into part[i], the LAT loads independent of each other; tail: the rest, again with static lanes.
+    auto term = [&](long long k) -> T {
         const long long ci = dense_M > 0 ? (k - beg) : (long long)col[k];
-        const T prod = Ops::mul(v, Bm[ci * P + j]);
+        return Ops::mul(val[k], Bm[ci * P + j]);
+    };
+    long long k = beg;
+    for (; k < end && lane != 0; k++) {
+        const T prod = term(k);
 #pragma unroll
-        for (int i = 0; i < LAT; i++)
+        for (int i = 1; i < LAT; i++)
             if (i == lane) part[i] = Ops::add(part[i], prod);
         lane = (lane + 1 == LAT) ? 0 : lane + 1;
     }
+    for (; k + LAT <= end; k += LAT) {
+        T prod[LAT];
+#pragma unroll
+        for (int i = 0; i < LAT; i++) prod[i] = term(k + i);
+#pragma unroll
+        for (int i = 0; i < LAT; i++) part[i] = Ops::add(part[i], prod[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < LAT - 1; i++)
+        if (k + i < end) part[i] = Ops::add(part[i], term(k + i));
     T acc = part[0];
 #pragma unroll
     for (int i = 1; i < LAT; i++) acc = Ops::add(acc, part[i]);
@@ -927,11 +944,13 @@ __device__ __forceinline__ unsigned h2_add(unsigned a, unsigned b) {
     return ftz_h2(*reinterpret_cast<const unsigned*>(&r));
 }
 
-template <int LAT>
+// DENSE: gemm_mode rows of dense_M entries (64-bit positions); otherwise CSR rows, whose positions fit an int
+template <int LAT, bool DENSE>
 __global__ void __launch_bounds__(256)
 stage_exact_f16x2_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const unsigned short* __restrict__ val,
                          const unsigned* __restrict__ Bm2,     // row-major, P/2 packed pairs per row
                          unsigned* __restrict__ out2, int nrows, int P2, int hw_threads, int sblock, int dense_M, int relu) {
+    typedef typename std::conditional<DENSE, long long, int>::type pos_t;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)nrows * P2) return;
     int r, j;                                          // 32-bit division whenever the index fits (the 64-bit one costs
@@ -945,25 +964,41 @@ stage_exact_f16x2_kernel(const int* __restrict__ rowptr, const int* __restrict__
     if (t > hw_threads - 1) t = hw_threads - 1;
     const int first_row = t * blk;
     const int base_row = first_row + ((r - first_row) / sblock) * sblock;
-    long long beg, end, base;
-    if (dense_M > 0) {
-        beg = (long long)r * dense_M; end = beg + dense_M; base = (long long)base_row * dense_M;
+    pos_t beg, end, base;
+    if (DENSE) {
+        beg = (pos_t)((long long)r * dense_M); end = beg + dense_M; base = (pos_t)((long long)base_row * dense_M);
     } else {
         beg = rowptr[r]; end = rowptr[r + 1]; base = rowptr[base_row];
     }
     unsigned part[LAT];
 #pragma unroll
     for (int i = 0; i < LAT; i++) part[i] = 0u;
-    int lane = (beg - base) < 0x7fffffffLL ? (int)((unsigned)(beg - base) % (unsigned)LAT) : (int)((beg - base) % LAT);
-    for (long long k = beg; k < end; k++) {
-        const unsigned v = (unsigned)OpsF16::ftz(val[k]);
-        const long long ci = dense_M > 0 ? (k - beg) : (long long)col[k];
-        const unsigned prod = h2_mul(v | (v << 16), ftz_h2(Bm2[ci * P2 + j]));
+    int lane = (int)((unsigned long long)(beg - base) % (unsigned)LAT);
+    const unsigned* bcol = Bm2 + j;
+    // head / body / tail as in stage_exact_kernel: a run-time lane only for the first entries of the row
+    auto term = [&](pos_t k) -> unsigned {
+        const unsigned v = (unsigned)OpsF16::ftz(__ldg(val + k));
+        const unsigned ci = DENSE ? (unsigned)(k - beg) : (unsigned)__ldg(col + k);
+        return h2_mul(v | (v << 16), ftz_h2(__ldg(bcol + (size_t)ci * (unsigned)P2)));
+    };
+    pos_t k = beg;
+    for (; k < end && lane != 0; k++) {
+        const unsigned prod = term(k);
 #pragma unroll
-        for (int i = 0; i < LAT; i++)
+        for (int i = 1; i < LAT; i++)
             if (i == lane) part[i] = h2_add(part[i], prod);
         lane = (lane + 1 == LAT) ? 0 : lane + 1;
     }
+    for (; k + LAT <= end; k += LAT) {
+        unsigned prod[LAT];
+#pragma unroll
+        for (int i = 0; i < LAT; i++) prod[i] = term(k + i);
+#pragma unroll
+        for (int i = 0; i < LAT; i++) part[i] = h2_add(part[i], prod[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < LAT - 1; i++)
+        if (k + i < end) part[i] = h2_add(part[i], term(k + i));
     unsigned acc = part[0];
 #pragma unroll
     for (int i = 1; i < LAT; i++) acc = h2_add(acc, part[i]);
