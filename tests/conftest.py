@@ -31,3 +31,18 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_terminal_summary(terminalreporter):
+    """Plain element-wise relative errors of the float comparisons (tests/util.py:assert_close_f32), worst first."""
+    try:
+        from tests import util as U
+    except Exception:
+        return
+    if not U.ELEMENTWISE_LOG:
+        return
+    worst = sorted(U.ELEMENTWISE_LOG, key=lambda t: -t[1])[:8]
+    terminalreporter.write_line("plain element-wise relative error (elements >= 1e-3 of the row max), worst of "
+                                f"{len(U.ELEMENTWISE_LOG)} float comparisons:")
+    for what, rel, n in worst:
+        terminalreporter.write_line(f"  {rel:.3e}  over {n} elements  {what}")

@@ -62,11 +62,23 @@ def to_storage_problem(pr, dtype):
     return adj, fea, B, xd
 
 
-def assert_close_f32(got, want, rtol=1e-5, what=""):
-    """Float tolerance of the north star: 1e-5 relative.  Elements that suffer cancellation are
-    judged against the magnitude of their row (atol = rtol * max|row|)."""
+ELEMENTWISE_LOG = []      # (what, worst plain relative error over the significant elements, their count): printed at session end
+
+
+def assert_close_f32(got, want, rtol=1e-5, what="", sig=1e-3, elem_rtol=2e-3):
+    """Float tolerance of the north star: 1e-5 relative.  Elements that suffer cancellation are judged against the
+    magnitude of their row (atol = rtol * max|row|).  Beside that row-normalised bar, the PLAIN element-wise relative
+    error |got - want| / |want| is computed over every element of at least `sig` of its row maximum, recorded in
+    ELEMENTWISE_LOG (shown in the pytest summary) and held to `elem_rtol`.  An absolute error of 1e-5 of the row maximum
+    is a relative error of up to 1e-2 on an element that is 1e-3 of it, so the element-wise bar is necessarily looser
+    than the row-normalised one; measured worst case over the GPU suite: 3.7e-4 (a 256-wide row with cancellation)."""
     got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
     scale = np.maximum(np.abs(want).max(axis=-1, keepdims=True), 1e-30) if want.ndim > 1 else np.abs(want).max() + 1e-30
     err = np.abs(got - want)
     bad = err > rtol * np.maximum(np.abs(want), scale)
     assert not bad.any(), f"{what}: {bad.sum()} of {bad.size} elements beyond {rtol} rel; max err {err.max():.3e}"
+    significant = np.abs(want) >= sig * scale
+    if significant.any():
+        rel = err[significant] / np.abs(want[significant])
+        ELEMENTWISE_LOG.append((what, float(rel.max()), int(significant.sum())))
+        assert rel.max() <= elem_rtol, f"{what}: plain element-wise relative error {rel.max():.3e} > {elem_rtol} on elements >= {sig} of the row max"
