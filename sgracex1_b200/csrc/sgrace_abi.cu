@@ -71,7 +71,9 @@ struct sgrace_handle {
     int overlap = 1;                            // SGRACE_OPT_OVERLAP
     cudaStream_t s_up = nullptr, s_down = nullptr;   // staging copies beside the kernels (created on first use)
     std::vector<cudaEvent_t> ev_pool;
-    uint64_t overlapped_starts = 0;
+    uint64_t overlapped_starts = 0, pipelined_starts = 0;
+    void* pipe_host = nullptr;                  // pinned: panel starts / maxima of start_pipelined
+    Scratch pipe_dev;
     int adj_plan = 0;                           // SGRACE_OPT_ADJ_PLAN (opt-in: measured slower than the gather kernel on Cora-size blocks)
     std::vector<AdjPlan> plans;                 // small cache of panel plans
     uint64_t plan_clock = 0, plan_builds = 0, panel_launches = 0;
@@ -1144,6 +1146,17 @@ const Buffer* find_buffer(const sgrace_handle* h, uint64_t a, size_t* offset) {
     return nullptr;
 }
 
+// largest column index referenced by each row panel of a CSR adjacency: panel i = non-zeros [k0[i], k0[i+1])
+__global__ void panel_maxcol_kernel(const int* __restrict__ col, const long long* __restrict__ k0, int npanels, int* __restrict__ out) {
+    const int i = blockIdx.y;
+    if (i >= npanels) return;
+    int m = -1;
+    for (long long k = k0[i] + (long long)blockIdx.x * blockDim.x + threadIdx.x; k < k0[i + 1]; k += (long long)gridDim.x * blockDim.x)
+        m = max(m, __ldg(col + k));
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m >= 0) atomicMax(out + i, m);
+}
+
 // host mirror -> device for bytes [skip, skip + bytes) behind device address addr, on stream st (0: the handle's)
 int stage_in(sgrace_handle* h, uint64_t addr, size_t bytes, size_t skip = 0, cudaStream_t st = nullptr) {
     size_t off;
@@ -1163,6 +1176,148 @@ int stage_out(sgrace_handle* h, uint64_t addr, size_t bytes, size_t skip = 0, cu
         return fail(h, SGRACE_EBOUNDS, "layer writes %zu bytes at buffer offset %zu but the allocation has %zu", skip + bytes,
                     off, b->bytes);
     CU(cudaMemcpyAsync((char*)b->host + off + skip, (char*)b->dev + off + skip, bytes, cudaMemcpyDeviceToHost, st ? st : h->stream));
+    return 0;
+}
+
+// Banded / block-diagonal adjacencies (batched graphs): the whole layer is pipelined in row chunks, so that D comes down
+// while the features are still going up.  The column array goes up first and a small kernel finds the largest column each
+// row panel references (exact, on the device); the host reads those K numbers, then queues: feature chunk c up -> feature
+// stage on chunk c -> every adjacency panel whose columns are now covered -> that panel of D down.  The order of the
+// launches follows the exact maxima, so the result does not depend on the guess that made us come here (a host sample of
+// the column array); a general graph simply runs all its panels after the last chunk.  -100: does not qualify.
+int start_pipelined(sgrace_handle* h, sgrace_layer_desc& d, uint64_t a_rpf, uint64_t a_cif, uint64_t a_vf, uint64_t a_rpa,
+                    uint64_t a_cia, uint64_t a_va, uint64_t a_b, uint64_t a_d, long long nnz_fea, long long nnz_adj) {
+    const size_t N = (size_t)d.N_adj, M = (size_t)d.M_fea, P = (size_t)d.P_w;
+    if (!h->overlap || h->mode != SGRACE_MODE_F32_FAST || h->index_format != 0 || h->agg_first || h->accumulate ||
+        h->peer_count > 0 || d.gemm_mode == 2 || d.gat_mode || nnz_adj <= 0)
+        return -100;
+    const size_t d_bytes = N * P * 4;
+    if (d_bytes < ((size_t)16 << 20) || (h->fused_small && d.N_adj <= h->fused_small)) return -100;
+    size_t off;
+    const Buffer* b_rpa = find_buffer(h, a_rpa, &off);
+    if (!b_rpa) return -100;
+    const int* rpa = (const int*)((const char*)b_rpa->host + off);
+    const Buffer* b_cia = find_buffer(h, a_cia, &off);
+    if (!b_cia || !find_buffer(h, a_va, &off) || !find_buffer(h, a_d, &off)) return -100;
+    find_buffer(h, a_cia, &off);
+    const int* cia = (const int*)((const char*)b_cia->host + off);
+    const int* rpf = nullptr;
+    if (d.gemm_mode == 0) {
+        const Buffer* b_rpf = find_buffer(h, a_rpf, &off);
+        if (!b_rpf || !find_buffer(h, a_cif, &off) || !find_buffer(h, a_vf, &off)) return -100;
+        find_buffer(h, a_rpf, &off);
+        rpf = (const int*)((const char*)b_rpf->host + off);
+        if (rpf[0] != 0) return -100;
+    } else if (!find_buffer(h, a_vf, &off)) return -100;
+    if (rpa[0] != 0) return -100;
+    // panels of D of about 24 MB (12 MB panels were measured no faster: twice the launches for half the tail)
+    int K = (int)((d_bytes + ((size_t)24 << 20) - 1) / ((size_t)24 << 20));
+    if (K < 4) K = 4;
+    if (K > 16) K = 16;
+    const size_t rows_per = ((N + K - 1) / K + 127) & ~(size_t)127;
+    K = (int)((N + rows_per - 1) / rows_per);
+    if (K < 3) return -100;
+    // host sample: does a panel look past the chunk after its own?  256 entries per panel, a few microseconds
+    for (int i = 0; i + 2 < K; i++) {
+        const size_t r0 = (size_t)i * rows_per, r1 = r0 + rows_per;
+        const long long k0 = rpa[r0], k1 = rpa[r1];
+        if (k0 < 0 || k1 < k0 || k1 > nnz_adj) return -100;
+        const long long limit = (long long)(r1 + rows_per);
+        for (int sidx = 0; sidx < 256 && k1 > k0; sidx++) {
+            const long long k = k0 + (long long)(((unsigned long long)sidx * 2654435761ull) % (unsigned long long)(k1 - k0));
+            if (cia[k] >= limit) return -100;
+        }
+    }
+    if (!h->s_up) CU(cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking));
+    if (!h->s_down) CU(cudaStreamCreateWithFlags(&h->s_down, cudaStreamNonBlocking));
+    while ((int)h->ev_pool.size() < 2 * 16 + 4) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->ev_pool.push_back(e);
+    }
+    cudaEvent_t ev_prev = h->ev_pool[32], ev_max = h->ev_pool[33], ev_down = h->ev_pool[34], ev_b = h->ev_pool[35];
+    if (!h->pipe_host) CU(cudaHostAlloc(&h->pipe_host, 512, cudaHostAllocDefault));
+    if (int rc = ensure(h, h->pipe_dev, 512)) return rc;
+    long long* k0_host = (long long*)h->pipe_host;              // [K + 1] panel starts, then [K] maxima (ints)
+    int* max_host = (int*)(k0_host + 17);
+    for (int i = 0; i <= K; i++) { const size_t r = (size_t)i * rows_per < N ? (size_t)i * rows_per : N; k0_host[i] = rpa[r]; }
+    long long* k0_dev = (long long*)h->pipe_dev.p;
+    int* max_dev = (int*)(k0_dev + 17);
+    CU(cudaEventRecord(ev_prev, h->stream));
+    CU(cudaStreamWaitEvent(h->s_up, ev_prev, 0));
+    CU(cudaStreamWaitEvent(h->s_down, ev_prev, 0));
+    // ---- uploads, all on s_up in the order they are needed ----
+    if (int rc = stage_in(h, a_cia, (size_t)nnz_adj * 4, 0, h->s_up)) return rc;
+    CU(cudaMemcpyAsync(k0_dev, k0_host, 17 * 8, cudaMemcpyHostToDevice, h->s_up));
+    CU(cudaMemsetAsync(max_dev, 0xff, 16 * 4, h->s_up));
+    panel_maxcol_kernel<<<dim3(64, K), 256, 0, h->s_up>>>(d.columnIndex_adj, k0_dev, K, max_dev);
+    h->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(max_host, max_dev, 16 * 4, cudaMemcpyDeviceToHost, h->s_up));
+    CU(cudaEventRecord(ev_max, h->s_up));
+    if (int rc = stage_in(h, a_rpa, (N + 1) * 4, 0, h->s_up)) return rc;
+    if (int rc = stage_in(h, a_va, (size_t)nnz_adj * 4, 0, h->s_up)) return rc;
+    if (int rc = stage_in(h, a_b, M * P * 4, 0, h->s_up)) return rc;
+    CU(cudaEventRecord(ev_b, h->s_up));
+    if (d.gemm_mode == 0) if (int rc = stage_in(h, a_rpf, (N + 1) * 4, 0, h->s_up)) return rc;
+    for (int c = 0; c < K; c++) {
+        const size_t r0 = (size_t)c * rows_per, r1 = r0 + rows_per < N ? r0 + rows_per : N;
+        if (d.gemm_mode == 0) {
+            const long long f0 = rpf[r0], f1 = rpf[r1];
+            if (f0 < 0 || f1 < f0 || f1 > nnz_fea) return fail(h, SGRACE_EBOUNDS, "feature row pointers not monotonic around row %zu", r0);
+            if (int rc = stage_in(h, a_cif, (size_t)(f1 - f0) * 4, (size_t)f0 * 4, h->s_up)) return rc;
+            if (int rc = stage_in(h, a_vf, (size_t)(f1 - f0) * 4, (size_t)f0 * 4, h->s_up)) return rc;
+        } else {
+            if (int rc = stage_in(h, a_vf, (r1 - r0) * M * 4, r0 * M * 4, h->s_up)) return rc;
+        }
+        CU(cudaEventRecord(h->ev_pool[c], h->s_up));
+    }
+    void* XW = d.XW;
+    if (!XW) {
+        if (int rc = ensure(h, h->xw, 4 * N * P + 16)) return rc;
+        XW = h->xw.p;
+    }
+    if (int rc = ensure(h, h->wrm, 4 * M * P)) return rc;
+    // ---- the K maxima (the column array has landed; the other uploads keep the copy engine busy meanwhile) ----
+    CU(cudaEventSynchronize(ev_max));
+    int need[16];                       // chunk that must be done before panel i may run
+    for (int i = 0; i < K; i++) {
+        const int mc = max_host[i];
+        if (mc >= (int)N) return fail(h, SGRACE_EBOUNDS, "adjacency column index %d out of range [0,%zu)", mc, N);
+        need[i] = mc < 0 ? 0 : (int)((size_t)mc / rows_per);
+    }
+    h->ev_valid = false;
+    CU(cudaEventRecord(h->ev[0], h->stream));
+    CU(cudaStreamWaitEvent(h->stream, ev_b, 0));                  // B has landed
+    if (int rc = transpose_b<float>(h, d.B, h->wrm.p, (int)M, (int)P)) return rc;
+    bool launched[16] = {false};
+    for (int c = 0; c < K; c++) {
+        const size_t r0 = (size_t)c * rows_per, r1 = r0 + rows_per < N ? r0 + rows_per : N;
+        CU(cudaStreamWaitEvent(h->stream, h->ev_pool[c], 0));
+        if (d.gemm_mode == 0) {
+            if (int rc = spmm_f32(h, d.rowPtr_fea + r0, d.columnIndex_fea, (const float*)d.values_fea, (const float*)h->wrm.p,
+                                  (float*)XW + r0 * P, (int)(r1 - r0), (int)P, 0, (long long)rpf[r1] - rpf[r0], (int)M, 0)) return rc;
+        } else {
+            if (int rc = dense_f32(h, (const float*)d.values_fea + r0 * M, (const float*)d.B, (float*)XW + r0 * P, (int)(r1 - r0),
+                                   (int)M, (int)P, 0)) return rc;
+        }
+        if (c == K - 1) CU(cudaEventRecord(h->ev[1], h->stream));
+        for (int i = 0; i < K; i++) {
+            if (launched[i] || need[i] > c) continue;
+            launched[i] = true;
+            const size_t a0 = (size_t)i * rows_per, a1 = a0 + rows_per < N ? a0 + rows_per : N;
+            if (int rc = spmm_f32(h, d.rowPtr_adj + a0, d.columnIndex_adj, (const float*)d.values_adj, (const float*)XW,
+                                  (float*)d.D + a0 * P, (int)(a1 - a0), (int)P, d.relu != 0, k0_host[i + 1] - k0_host[i], 0, 1, 0)) return rc;
+            CU(cudaEventRecord(h->ev_pool[16 + i], h->stream));
+            CU(cudaStreamWaitEvent(h->s_down, h->ev_pool[16 + i], 0));
+            if (int rc = stage_out(h, a_d, (a1 - a0) * P * 4, a0 * P * 4, h->s_down)) return rc;
+        }
+    }
+    CU(cudaEventRecord(h->ev[2], h->stream));
+    CU(cudaEventRecord(ev_down, h->s_down));
+    CU(cudaStreamWaitEvent(h->stream, ev_down, 0));
+    h->overlapped_starts++;
+    h->pipelined_starts++;
     return 0;
 }
 
@@ -1312,6 +1467,8 @@ int sgrace_destroy(sgrace_handle* h) {
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->s_up) { cudaStreamSynchronize(h->s_up); cudaStreamDestroy(h->s_up); }
     if (h->s_down) { cudaStreamSynchronize(h->s_down); cudaStreamDestroy(h->s_down); }
+    if (h->pipe_host) cudaFreeHost(h->pipe_host);
+    if (h->pipe_dev.p) cudaFree(h->pipe_dev.p);
     Scratch* all[] = {&h->plan_a, &h->plan_b, &h->plan_c, &h->plan_d, &h->plan_flag, &h->plan_starts, &h->plan_tmp, &h->wrm, &h->ax, &h->long_partial, &h->long_done, &h->xw, &h->wq, &h->s1, &h->s2, &h->rp_fea, &h->rp_adj, &h->lists, &h->counters, &h->prep_keys, &h->prep_ids, &h->prep_misc, &h->prep_tmp};
     for (Scratch* s : all) if (s->p) cudaFree(s->p);
     if (h->max_fea_dev) cudaFree(h->max_fea_dev);
@@ -1460,6 +1617,7 @@ int sgrace_get_option(sgrace_handle* h, int key, int64_t* v) {
         case SGRACE_OPT_ADJ_PLAN: *v = h->adj_plan; break;
         case SGRACE_OPT_OVERLAP: *v = h->overlap; break;
         case SGRACE_OPT_OVERLAPPED_STARTS: *v = (int64_t)h->overlapped_starts; break;
+        case SGRACE_OPT_PIPELINED_STARTS: *v = (int64_t)h->pipelined_starts; break;
         case SGRACE_OPT_PANEL_LAUNCHES: *v = (int64_t)h->panel_launches; break;
         case SGRACE_OPT_PLAN_BUILDS: *v = (int64_t)h->plan_builds; break;
         default: return fail(h, SGRACE_EINVAL, "unknown option %d", key);
@@ -1845,7 +2003,8 @@ int sgrace_start(sgrace_handle* h) {
 
     CU(cudaEventRecord(h->ev[4], h->stream));
     if (h->staging && !(full && h->qbits > 0)) {
-        const int rc = start_overlapped(h, d, a_rpf, a_cif, a_vf, a_rpa, a_cia, a_va, a_b, a_d, nnz_fea, nnz_adj);
+        int rc = start_pipelined(h, d, a_rpf, a_cif, a_vf, a_rpa, a_cia, a_va, a_b, a_d, nnz_fea, nnz_adj);
+        if (rc == -100) rc = start_overlapped(h, d, a_rpf, a_cif, a_vf, a_rpa, a_cia, a_va, a_b, a_d, nnz_fea, nnz_adj);
         if (rc != -100) {
             if (rc) return rc;
             const uint64_t a_prof = reg64(h, SGRACE_REG_PROFILING);

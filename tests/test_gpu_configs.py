@@ -89,16 +89,21 @@ def test_benchmark_scale_properties(ip):
 
 
 @pytest.mark.parametrize("dense", [False, True])
-def test_overlapped_staging_equals_the_serial_path(ip, dense):
-    """sgrace_start with host buffers on a layer whose D exceeds 16 MB: the adjacency upload in row panels, the
-    panel-by-panel aggregation and the panelled download of D (SGRACE_OPT_OVERLAP) give the bits of the serial path,
-    twice in a row (buffers and events are reused)."""
+@pytest.mark.parametrize("banded", [True, False])
+def test_overlapped_staging_equals_the_serial_path(ip, dense, banded):
+    """sgrace_start with host buffers on a layer whose D exceeds 16 MB (SGRACE_OPT_OVERLAP).  A block-diagonal batch is
+    pipelined in row chunks (features up -> FEA -> the adjacency panels whose columns are covered -> D down); a graph
+    whose rows reference columns anywhere takes the panelled adjacency upload / download after one feature stage.
+    Both give the bits of the serial path, twice in a row (buffers and events are reused)."""
     from sgracex1_b200.driver import HostLayer
     probs = [G.cora_shape(seed=s, n=2708, m=96, nnz_fea=9000) for s in range(3)]
     b = G.block_diagonal(probs, 120)
     assert b.N * b.P * 4 >= 16 << 20
-    adj, fea = (b.adj_rowptr, b.adj_col, b.adj_val), (b.fea_rowptr, b.fea_col, b.fea_val)
     rng = np.random.default_rng(3)
+    adj, fea = (b.adj_rowptr, b.adj_col, b.adj_val), (b.fea_rowptr, b.fea_col, b.fea_val)
+    if not banded:
+        ci = rng.integers(0, b.N, size=b.nnz_adj).astype(np.int32)       # columns anywhere (order within a row is free)
+        adj = (b.adj_rowptr, ci, b.adj_val)
     xd = rng.standard_normal((b.N, 8)).astype(np.float32) if dense else None
     M = 8 if dense else b.M
     B = (rng.uniform(-0.3, 0.3, size=(b.P, 8)).astype(np.float32).reshape(-1)) if dense else b.B
@@ -107,6 +112,7 @@ def test_overlapped_staging_equals_the_serial_path(ip, dense):
     for overlap in (0, 1, 1):
         ip.configure(mode=_lib.MODE_F32_FAST, staging=1, index_format=0, overlap=overlap)
         before = ip.handle.get_option(_lib.OPT_OVERLAPPED_STARTS)
+        before_p = ip.handle.get_option(_lib.OPT_PIPELINED_STARTS)
         if dense:
             hl.load(N=b.N, M=M, P=b.P, adj=adj, x_dense=xd, B=B, relu=1)
         else:
@@ -114,6 +120,7 @@ def test_overlapped_staging_equals_the_serial_path(ip, dense):
         hl.D[:] = -3.0
         outs.append(hl.run().copy())
         assert ip.handle.get_option(_lib.OPT_OVERLAPPED_STARTS) - before == overlap
+        assert ip.handle.get_option(_lib.OPT_PIPELINED_STARTS) - before_p == (overlap if banded else 0)
     hl.free()
     ip.configure(overlap=1)
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
