@@ -2003,10 +2003,21 @@ int sgrace_start(sgrace_handle* h) {
 
     CU(cudaEventRecord(h->ev[4], h->stream));
     if (h->staging && !(full && h->qbits > 0)) {
-        int rc = start_pipelined(h, d, a_rpf, a_cif, a_vf, a_rpa, a_cia, a_va, a_b, a_d, nnz_fea, nnz_adj);
-        if (rc == -100) rc = start_overlapped(h, d, a_rpf, a_cif, a_vf, a_rpa, a_cia, a_va, a_b, a_d, nnz_fea, nnz_adj);
+        // the side-stream paths wait on an event from the host: not inside a stream capture
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        CU(cudaStreamIsCapturing(h->stream, &cap));
+        int rc = -100;
+        if (cap == cudaStreamCaptureStatusNone) {
+            rc = start_pipelined(h, d, a_rpf, a_cif, a_vf, a_rpa, a_cia, a_va, a_b, a_d, nnz_fea, nnz_adj);
+            if (rc == -100) rc = start_overlapped(h, d, a_rpf, a_cif, a_vf, a_rpa, a_cia, a_va, a_b, a_d, nnz_fea, nnz_adj);
+        }
         if (rc != -100) {
-            if (rc) return rc;
+            if (rc) {
+                // an error after copies were queued on the side streams: let them drain before anything else touches the buffers
+                if (h->s_up) cudaStreamSynchronize(h->s_up);
+                if (h->s_down) cudaStreamSynchronize(h->s_down);
+                return rc;
+            }
             const uint64_t a_prof = reg64(h, SGRACE_REG_PROFILING);
             size_t off;
             const Buffer* pb = find_buffer(h, a_prof, &off);
