@@ -64,10 +64,10 @@ def spmm_ref(adj, xw, relu):
     return np.maximum(out, 0) if relu else out
 
 
-@pytest.mark.parametrize("P", [16, 64, 8, 128])
+@pytest.mark.parametrize("P", [16, 64, 8, 128, 4, 256])
 def test_panel_adj_bit_equal_to_gather(ip, P):
     rng = np.random.default_rng(P)
-    sizes = rng.integers(40, 420 if P <= 64 else 300, size=400)
+    sizes = rng.integers(40, 420 if P <= 64 else (300 if P <= 128 else 150), size=400 if P <= 128 else 700)
     N, adj = batched_adjacency(sizes, rng, hub_every=37)
     xw = rng.standard_normal((N, P)).astype(np.float32)
     for relu in (1, 0):
