@@ -102,6 +102,36 @@ def profiled_traffic(stage):
         return None, None, None
 
 
+def host_memory_near_gpu(local):
+    """Multi-rank runs: prefer host memory (the pinned staging buffers) and CPU cores on the NUMA node of this rank's
+    GPU, so that eight ranks do not all stage through one socket.  Best effort: returns what was done."""
+    info = {"gpu_node": None, "policy": "unchanged"}
+    try:
+        import ctypes
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        info["gpu_node"] = node
+        if node < 0 or not os.path.isdir(f"/sys/devices/system/node/node{node}"):
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["cpus"] = len(allowed)
+        libc = ctypes.CDLL(None, use_errno=True)
+        mask = ctypes.c_ulong(1 << node)
+        rc = libc.syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(64))      # set_mempolicy(MPOL_PREFERRED, node)
+        info["policy"] = "preferred" if rc == 0 else f"set_mempolicy errno {ctypes.get_errno()}"
+    except Exception as ex:  # noqa: BLE001
+        info["policy"] = f"unavailable ({type(ex).__name__})"
+    return info
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -319,6 +349,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = host_memory_near_gpu(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
 
@@ -457,6 +488,7 @@ def run_ours(args):
                              "launches: launch-latency-bound (1.1 MB of traffic = 0.17 us of HBM time); reference FPGA best "
                              "0.68 ms layer 1 (paper Table 4)"},
             "clocks": clocks,
+            **({"host_numa": numa} if numa else {}),
         }
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
