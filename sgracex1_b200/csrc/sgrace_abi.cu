@@ -1146,6 +1146,12 @@ const Buffer* find_buffer(const sgrace_handle* h, uint64_t a, size_t* offset) {
     return nullptr;
 }
 
+const void* host_view(const sgrace_handle* h, uint64_t addr) {
+    size_t off;
+    const Buffer* b = find_buffer(h, addr, &off);
+    return b ? (const char*)b->host + off : nullptr;
+}
+
 // largest column index referenced by each row panel of a CSR adjacency: panel i = non-zeros [k0[i], k0[i+1])
 __global__ void panel_maxcol_kernel(const int* __restrict__ col, const long long* __restrict__ k0, int npanels, int* __restrict__ out) {
     const int i = blockIdx.y;
@@ -1193,22 +1199,16 @@ int start_pipelined(sgrace_handle* h, sgrace_layer_desc& d, uint64_t a_rpf, uint
         return -100;
     const size_t d_bytes = N * P * 4;
     if (d_bytes < ((size_t)16 << 20) || (h->fused_small && d.N_adj <= h->fused_small)) return -100;
-    size_t off;
-    const Buffer* b_rpa = find_buffer(h, a_rpa, &off);
-    if (!b_rpa) return -100;
-    const int* rpa = (const int*)((const char*)b_rpa->host + off);
-    const Buffer* b_cia = find_buffer(h, a_cia, &off);
-    if (!b_cia || !find_buffer(h, a_va, &off) || !find_buffer(h, a_d, &off)) return -100;
-    find_buffer(h, a_cia, &off);
-    const int* cia = (const int*)((const char*)b_cia->host + off);
+    // host mirrors of the index arrays (the chunk boundaries are read from them); every operand must sit in a buffer
+    // from sgrace_alloc
+    const int* rpa = (const int*)host_view(h, a_rpa);
+    const int* cia = (const int*)host_view(h, a_cia);
+    if (!rpa || !cia || !host_view(h, a_va) || !host_view(h, a_d) || !host_view(h, a_vf) || !host_view(h, a_b)) return -100;
     const int* rpf = nullptr;
     if (d.gemm_mode == 0) {
-        const Buffer* b_rpf = find_buffer(h, a_rpf, &off);
-        if (!b_rpf || !find_buffer(h, a_cif, &off) || !find_buffer(h, a_vf, &off)) return -100;
-        find_buffer(h, a_rpf, &off);
-        rpf = (const int*)((const char*)b_rpf->host + off);
-        if (rpf[0] != 0) return -100;
-    } else if (!find_buffer(h, a_vf, &off)) return -100;
+        rpf = (const int*)host_view(h, a_rpf);
+        if (!rpf || !host_view(h, a_cif) || rpf[0] != 0) return -100;
+    }
     if (rpa[0] != 0) return -100;
     // panels of D of about 24 MB (12 MB panels were measured no faster: twice the launches for half the tail)
     int K = (int)((d_bytes + ((size_t)24 << 20) - 1) / ((size_t)24 << 20));
@@ -1334,11 +1334,8 @@ int start_overlapped(sgrace_handle* h, sgrace_layer_desc& d, uint64_t a_rpf, uin
         return -100;
     const size_t d_bytes = N * P * 4;
     if (d_bytes < ((size_t)16 << 20) || (h->fused_small && d.N_adj <= h->fused_small)) return -100;
-    size_t off_rp;
-    const Buffer* brp = find_buffer(h, a_rpa, &off_rp);
-    if (!brp || !find_buffer(h, a_cia, &off_rp) || !find_buffer(h, a_va, &off_rp) || !find_buffer(h, a_d, &off_rp)) return -100;
-    const Buffer* b0 = find_buffer(h, a_rpa, &off_rp);
-    const int* rp_host = (const int*)((const char*)b0->host + off_rp);
+    const int* rp_host = (const int*)host_view(h, a_rpa);
+    if (!rp_host || !host_view(h, a_cia) || !host_view(h, a_va) || !host_view(h, a_d)) return -100;
     if (rp_host[0] != 0) return -100;
     // panels of D of about 24 MB, row counts a multiple of 128 (the row-pointer slice of a panel stays 16-byte aligned)
     int K = (int)((d_bytes + ((size_t)24 << 20) - 1) / ((size_t)24 << 20));
@@ -1405,11 +1402,6 @@ int start_overlapped(sgrace_handle* h, sgrace_layer_desc& d, uint64_t a_rpf, uin
     CU(cudaStreamWaitEvent(h->stream, ev_down, 0));     // the handle's stream ends when the last panel of D is on the host
     h->overlapped_starts++;
     return 0;
-}
-const void* host_view(const sgrace_handle* h, uint64_t addr) {
-    size_t off;
-    const Buffer* b = find_buffer(h, addr, &off);
-    return b ? (const char*)b->host + off : nullptr;
 }
 
 int validate_csr_host(sgrace_handle* h, const int* rp, const int* ci, int n, int ncols, const char* what) {
