@@ -122,6 +122,16 @@ def test_stale_plan_and_unfit_graphs_stay_correct(ip):
     assert ip.handle.get_option(_lib.OPT_PANEL_LAUNCHES) == before + 1      # the cached plan was used
     ip.configure(adj_plan=0)
     U.assert_close_f32(D.cpu().numpy(), spmm_ref((adj[0], ci2, adj[2]), xw, 1).astype(np.float32), what="stale plan")
+    # adj_plan = 2: the plan is analysed at every launch (the new contents are block-diagonal again after the restore)
+    t[1].copy_(torch.from_numpy(adj[1]))
+    builds = ip.handle.get_option(_lib.OPT_PLAN_BUILDS)
+    ip.configure(mode=_lib.MODE_F32_FAST, staging=0, index_format=0, adj_plan=2)
+    for _ in range(2):
+        ip.handle.adj_run(d, x.data_ptr(), N)
+    torch.cuda.synchronize()
+    ip.configure(adj_plan=0)
+    assert ip.handle.get_option(_lib.OPT_PLAN_BUILDS) == builds + 2
+    assert np.array_equal(D.cpu().numpy(), got)
     # one connected random graph: no diagonal blocks -> the plan is not usable and the gather kernel runs
     N2 = 20000
     rp = np.arange(0, 4 * N2 + 1, 4, dtype=np.int32)
