@@ -99,6 +99,8 @@ enum {
     SGRACE_OPT_OVERLAP = 23,        /* staging mode, float32 layers whose D is at least 16 MB: 1 (default) the adjacency goes up in
                                        row panels on a second stream, the aggregation runs panel by panel and each panel of D
                                        goes down on a third stream under the next upload; 0: all copies in, kernels, copies out */
+    SGRACE_OPT_PUSH_CTAS = 26,      /* CTAs of sgrace_halo_push (0 = default, four per SM).  One per SM when the push runs beside
+                                       the aggregation of the owned columns: it then leaves the SMs to that kernel              */
     SGRACE_OPT_PIPELINED_STARTS = 25,  /* read-only: of those, starts pipelined in row chunks (banded / block-diagonal adjacency) */
     SGRACE_OPT_OVERLAPPED_STARTS = 24, /* read-only: starts that took the overlapped path                                   */
     SGRACE_OPT_PANEL_LAUNCHES = 21, /* read-only: launches of the panel kernel so far                                  */

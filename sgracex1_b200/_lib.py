@@ -15,7 +15,7 @@ MODE_F32_FAST, MODE_F32_CSIM, MODE_F16_CSIM, MODE_FIX16_CSIM, MODE_FULL = 0, 1, 
 (OPT_MODE, OPT_SPMM_BLOCK, OPT_LAT_FEA, OPT_LAT_ADJ, OPT_FEA_THREADS, OPT_ADJ_THREADS,
  OPT_USE_SBLOCKS, OPT_INDEX_FORMAT, OPT_QBITS, OPT_STAGING, OPT_LONG_ROW, OPT_LEAKY_ALPHA_BITS,
  OPT_VALIDATE, OPT_DENSE_TC, OPT_STREAM_KERNEL, OPT_AGG_FIRST, OPT_ACCUMULATE, OPT_FUSED_SMALL, OPT_ROW_OFFSET,
- OPT_ADJ_PLAN, OPT_PANEL_LAUNCHES, OPT_PLAN_BUILDS, OPT_OVERLAP, OPT_OVERLAPPED_STARTS, OPT_PIPELINED_STARTS) = range(1, 26)
+ OPT_ADJ_PLAN, OPT_PANEL_LAUNCHES, OPT_PLAN_BUILDS, OPT_OVERLAP, OPT_OVERLAPPED_STARTS, OPT_PIPELINED_STARTS, OPT_PUSH_CTAS) = range(1, 27)
 REG_CTRL, REG_MAX_FEA = 0x00, 0x70
 
 EXPORTS = (

@@ -69,6 +69,7 @@ struct sgrace_handle {
     int spmm_block = 1, lat_fea = 0, lat_adj = 0, fea_threads = 1, adj_threads = 1, use_sblocks = 0;
     int index_format = 0, qbits = 8, staging = 1, long_row = 512, validate = 0, dense_tc = 1, stream_kernel = 1, agg_first = 0, accumulate = 0;
     int overlap = 1;                            // SGRACE_OPT_OVERLAP
+    int push_ctas = 0;                          // SGRACE_OPT_PUSH_CTAS
     cudaStream_t s_up = nullptr, s_down = nullptr;   // staging copies beside the kernels (created on first use)
     std::vector<cudaEvent_t> ev_pool;
     uint64_t overlapped_starts = 0, pipelined_starts = 0;
@@ -96,7 +97,8 @@ struct sgrace_handle {
     struct StreamTune {
         int c_s = 0, c_g = 0, g_s = 0, g_g = 0, s_s = 0, s_g = 0, tr_s = 0, tr_g = 0, threads_s = 0, threads_g = 0;
         int ctas = 0, nosmem = 0, long_noseg = 0, live = 0;
-        int p_c = 0, p_g = 0, p_s = 0, p_tr = 0, p_ncw = 0, p_long = 0, p_dbg = 0;      // panel kernel (SGRACE_PANEL_*)
+        int p_c = 0, p_g = 0, p_s = 0, p_tr = 0, p_ncw = 0, p_long = 0, p_dbg = 0;
+        int push_ctas = 0;                                         // halo push kernel: CTAs (SGRACE_HALO_PUSH_CTAS; 0 = 4 per SM)      // panel kernel (SGRACE_PANEL_*)
     } tune;
     std::map<std::pair<const void*, uint64_t>, int> launch_cfg;   // (kernel, threads << 32 | smem) -> resident CTAs per SM
     int* max_fea_dev = nullptr;
@@ -170,6 +172,7 @@ void load_tune(sgrace_handle* h) {
     t.live = env_int("SGRACE_TUNE_LIVE", 0);
     t.p_c = env_int("SGRACE_PANEL_C", 0); t.p_g = env_int("SGRACE_PANEL_G", 0); t.p_s = env_int("SGRACE_PANEL_S", 0);
     t.p_tr = env_int("SGRACE_PANEL_TR", 0); t.p_ncw = env_int("SGRACE_PANEL_NCW", 0); t.p_long = env_int("SGRACE_PANEL_LONG", 0); t.p_dbg = env_int("SGRACE_PANEL_DBG", 0);
+    t.push_ctas = env_int("SGRACE_HALO_PUSH_CTAS", 0);
 }
 
 // resident CTAs per SM of `kern` at this block size / dynamic shared memory; the attribute call and the occupancy
@@ -1579,6 +1582,7 @@ int sgrace_set_option(sgrace_handle* h, int key, int64_t v) {
         case SGRACE_OPT_ROW_OFFSET: if (v < 0) return fail(h, SGRACE_EINVAL, "row_offset < 0"); h->row_offset = (int)v; break;
         case SGRACE_OPT_ADJ_PLAN: if (v < 0 || v > 2) return fail(h, SGRACE_EINVAL, "adj_plan must be 0,1,2"); h->adj_plan = (int)v; break;
         case SGRACE_OPT_OVERLAP: h->overlap = v != 0; break;
+        case SGRACE_OPT_PUSH_CTAS: if (v < 0 || v > 65535) return fail(h, SGRACE_EINVAL, "push_ctas out of range"); h->push_ctas = (int)v; break;
         default: return fail(h, SGRACE_EINVAL, "unknown option %d", key);
     }
     return SGRACE_OK;
@@ -1608,6 +1612,7 @@ int sgrace_get_option(sgrace_handle* h, int key, int64_t* v) {
         case SGRACE_OPT_ROW_OFFSET: *v = h->row_offset; break;
         case SGRACE_OPT_ADJ_PLAN: *v = h->adj_plan; break;
         case SGRACE_OPT_OVERLAP: *v = h->overlap; break;
+        case SGRACE_OPT_PUSH_CTAS: *v = h->push_ctas; break;
         case SGRACE_OPT_OVERLAPPED_STARTS: *v = (int64_t)h->overlapped_starts; break;
         case SGRACE_OPT_PIPELINED_STARTS: *v = (int64_t)h->pipelined_starts; break;
         case SGRACE_OPT_PANEL_LAUNCHES: *v = (int64_t)h->panel_launches; break;
@@ -1810,12 +1815,15 @@ int sgrace_halo_push(sgrace_handle* h, const void* local, int32_t width, int32_t
         total_rows += counts[d];
     }
     pt.start[n_dst] = total_rows;
+    pt.rot = n_dst > 0 ? h->device % n_dst : 0;
     if (total_rows == 0) return SGRACE_OK;
     const size_t smem = (size_t)2 * HALO_CHUNK * width * 4;
     if (smem > 200 * 1024) return fail(h, SGRACE_EUNSUPPORTED, "halo push: rows wider than 400 floats are not supported");
     CU(cudaFuncSetAttribute(halo_push_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (h->tune.live) load_tune(h);
     long long grid = total_rows / HALO_CHUNK + n_dst;
-    if (grid > (long long)h->num_sms * 4) grid = (long long)h->num_sms * 4;
+    const long long cap = h->tune.push_ctas > 0 ? h->tune.push_ctas : (h->push_ctas > 0 ? h->push_ctas : (long long)h->num_sms * 4);
+    if (grid > cap) grid = cap;
     halo_push_kernel<<<(int)grid, 256, smem, h->stream>>>(pt, (const float4*)local, width / 4);
     h->launches++;
     CU(cudaGetLastError());

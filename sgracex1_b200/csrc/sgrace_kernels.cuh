@@ -616,6 +616,7 @@ struct PushTable {
     float4* dst[8];
     long long start[9];     // prefix of rows over the segments
     int count;
+    int rot;                // first segment a CTA serves: different on every GPU, so that the GPUs do not all push to the same peer at once
 };
 // A CTA packs HALO_CHUNK consecutive destination slots into shared memory (scattered 16-byte reads
 // of local rows) and ships them with ONE bulk store (cp.async.bulk shared -> peer global, TMA over
@@ -626,22 +627,21 @@ constexpr int HALO_CHUNK = 64;
 __global__ void __launch_bounds__(256)
 halo_push_kernel(const PushTable pt, const float4* __restrict__ local, int W4) {
     extern __shared__ __align__(128) float4 hbuf[];          // [2][HALO_CHUNK * W4]
-    // chunks are numbered segment by segment
-    long long cstart[9];
-    cstart[0] = 0;
+    // chunk v of the launch is chunk v / count of segment (v + rot) mod count: consecutive CTAs push to different peers
+    // (segment-by-segment order had every GPU push to the same peer at once: one ingress port busy, seven idle)
+    const int nd = pt.count;
+    long long maxch = 0;
 #pragma unroll
     for (int d = 0; d < 8; d++) {
-        const long long n = d < pt.count ? pt.start[d + 1] - pt.start[d] : 0;
-        cstart[d + 1] = cstart[d] + (n + HALO_CHUNK - 1) / HALO_CHUNK;
+        const long long n = d < nd ? pt.start[d + 1] - pt.start[d] : 0;
+        maxch = max(maxch, (n + HALO_CHUNK - 1) / HALO_CHUNK);
     }
-    const long long nchunks = cstart[8];
     int buf = 0;
-    for (long long c = blockIdx.x; c < nchunks; c += gridDim.x, buf ^= 1) {
-        int d = 0;
-#pragma unroll
-        for (int k = 1; k < 8; k++) d += (c >= cstart[k]) ? 1 : 0;
-        const long long j0 = (c - cstart[d]) * HALO_CHUNK;
+    for (long long v = blockIdx.x; v < maxch * nd; v += gridDim.x) {
+        const int d = (int)((v + pt.rot) % nd);
+        const long long j0 = (v / nd) * HALO_CHUNK;
         const long long nseg = pt.start[d + 1] - pt.start[d];
+        if (j0 >= nseg) continue;
         const int rows_here = (int)min((long long)HALO_CHUNK, nseg - j0);
         float4* sb = hbuf + (size_t)buf * HALO_CHUNK * W4;
         // the bulk store issued two iterations ago from this buffer must have finished reading it
@@ -662,6 +662,7 @@ halo_push_kernel(const PushTable pt, const float4* __restrict__ local, int W4) {
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
+        buf ^= 1;
     }
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }

@@ -401,9 +401,35 @@ class HaloLayer:
         n = self.hi - self.lo
         t = torch.empty(n, self.width, dtype=torch.float32, device=self.buf.device)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)] if timing is not None else None
-        mode = os.environ.get("SGRACE_HALO_EXCHANGE", "dma")      # dma | a2a | push | pull
+        mode = os.environ.get("SGRACE_HALO_EXCHANGE", "pushf")      # dma | pushf | a2a | push | pull
         dma = self.push is not None and mode == "dma"
-        overlap = self.overlap or (dma and os.environ.get("SGRACE_HALO_OVERLAP") != "0")
+        pushf = self.push is not None and mode == "pushf"
+        overlap = self.overlap or ((dma or pushf) and os.environ.get("SGRACE_HALO_OVERLAP") != "0")
+        if pushf:
+            # SM push straight into the peers' halo regions (halo_push_kernel: rows packed in shared memory, one bulk
+            # store per 64 destination slots, consecutive CTAs serving different peers), then one flag word per peer --
+            # stream memory operations behind the kernel, whose last instruction waits for its bulk stores.  No NCCL
+            # kernel, so nothing of the exchange needs an SM once the push kernel has finished.
+            rows_t, counts, dsts = self.push
+            from . import _lib
+            if not getattr(self, "_push_ctas_set", False):
+                # one CTA per SM: beside the aggregation kernel the push then reaches the same 0.42-0.46 ms as with
+                # four and slows the aggregation least (8 GPUs, products shape: 1.05 ms per layer against 1.12 / 1.25)
+                self.hh.set_option(_lib.OPT_PUSH_CTAS, torch.cuda.get_device_properties(self.buf.device).multi_processor_count)
+                self._push_ctas_set = True
+            self.ev_ready.record(self.s_main)
+            self.s_halo.wait_event(self.ev_ready)
+            if ev: ev[4].record(self.s_halo)
+            self.hh.halo_push(self.local.data_ptr(), self.width, [t_.data_ptr() for t_ in rows_t], counts, dsts)
+            self.epoch += 1
+            for r in range(self.world):
+                if r != self.rank:
+                    self.hh.peer_signal(self.flag_bases[r] + 4 * self.rank, self.epoch)
+            if ev: ev[0].record(self.s_main)
+            if overlap:
+                self._adj(self.a_loc, t, False)
+                if ev: ev[1].record(self.s_main)
+            return dict(t=t, ev=ev, dma=True, overlap=overlap, timing=timing)
         if dma:
             # pack on the main stream (it must not queue behind the aggregation kernel, which holds every SM);
             # everything that follows on the halo stream is copy-engine work and stream memory operations
@@ -828,6 +854,8 @@ def bench_products(args):
         for var in os.environ["SGRACE_HALO_SWEEP"].split(","):
             vm, vs, vo, vk = var.split(":")
             os.environ.update(SGRACE_HALO_EXCHANGE=vm, SGRACE_HALO_DMA_STREAMS=vs, SGRACE_HALO_OVERLAP=vo, SGRACE_HALO_REMOTE_KERNEL=vk)
+            if vm.startswith("push"):       # second field = CTAs of the push kernel per SM (needs SGRACE_TUNE_LIVE=1 in the environment)
+                os.environ["SGRACE_HALO_PUSH_CTAS"] = str(int(vs) * 148)
             layer.overlap = vo == "1"
             for _ in range(3):
                 step()
@@ -970,8 +998,10 @@ def products_strong_record(steps, warmup, rank, world, local, scale=1.0, sample_
     halo_bytes = int(layer.n_halo * M * 4)
     hb = torch.tensor([float(halo_bytes)], dtype=torch.float64, device=dev)
     dist.all_reduce(hb, op=dist.ReduceOp.MAX)
-    res["agg_first"] = {"ms_n": ms, "exchange": "halo rows of X over NVLink (copy engines + stream flag waits), overlapped with the "
-                        "aggregation of the owned columns" + (f", pipelined over {halo_chunks} row chunks" if halo_chunks > 1 else ""),
+    res["agg_first"] = {"ms_n": ms, "exchange": ("halo rows of X over NVLink (" + {"pushf": "SM push with bulk stores into the peers' halo regions + flag words",
+                                                                        "dma": "copy engines + flag words"}.get(
+                            os.environ.get("SGRACE_HALO_EXCHANGE", "pushf"), os.environ.get("SGRACE_HALO_EXCHANGE", "pushf")) +
+                                     " and stream waits), overlapped with the aggregation of the owned columns") + (f", pipelined over {halo_chunks} row chunks" if halo_chunks > 1 else ""),
                         "exchanged_bytes_per_gpu": int(hb.item()), "exchange_ms": exch_ms,
                         "exchange_gbs_per_gpu": (hb.item() / (exch_ms * 1e-3) / 1e9) if exch_ms else None}
     samples["agg_first"] = out[pick].clone()

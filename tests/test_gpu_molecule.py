@@ -221,11 +221,13 @@ def test_halo_layer_three_emulated_ranks_on_one_gpu():
     hm.peer_release()
 
 
-def test_halo_layer_copy_engine_exchange_three_emulated_ranks(monkeypatch):
-    """The SM-free exchange (pack, copy-engine transfers, flag words, stream waits) with the owned columns
-    aggregated while the halo travels: three emulated ranks on one GPU, each with its own streams and
-    handles, two layers back to back (the flags carry an epoch)."""
-    monkeypatch.setenv("SGRACE_HALO_EXCHANGE", "dma")
+@pytest.mark.parametrize("exchange", ["dma", "pushf"])
+def test_halo_layer_copy_engine_exchange_three_emulated_ranks(monkeypatch, exchange):
+    """The exchanges that signal with flag words and stream waits -- "dma": pack, copy-engine transfers (no SM);
+    "pushf": SM push straight into the peers' halo regions -- with the owned columns aggregated while the halo
+    travels: three emulated ranks on one GPU, each with its own streams and handles, two layers back to back (the
+    flags carry an epoch)."""
+    monkeypatch.setenv("SGRACE_HALO_EXCHANGE", exchange)
     n, m, p = 3000, 100, 256
     pr = U.random_problem(29, n=n, m=m, p=p, avg_deg=8)
     rp, ci, va = pr["adj"]
