@@ -28,6 +28,19 @@ def test_library_exports_every_declared_symbol():
     assert set(_lib.EXPORTS) == set(syms)
 
 
+def test_option_numbers_match_the_python_binding():
+    """Every SGRACE_OPT_* of the header has the same number as _lib.OPT_* (both lists are written by hand), and the
+    option keys `configure()` accepts exist."""
+    hdr = open(os.path.join(ROOT, "include", "sgrace_b200.h")).read()
+    opts = dict(re.findall(r"SGRACE_OPT_([A-Z0-9_]+)\s*=\s*(\d+)", hdr))
+    assert len(opts) >= 26 and len(set(opts.values())) == len(opts)          # no number used twice
+    for name, value in opts.items():
+        assert getattr(_lib, "OPT_" + name) == int(value), name
+    modes = dict(re.findall(r"SGRACE_MODE_([A-Z0-9_]+)\s*=\s*(\d+)", hdr))
+    for name, value in modes.items():
+        assert getattr(_lib, "MODE_" + name) == int(value), name
+
+
 def test_register_offsets_follow_the_hardware_handoff_file():
     # spot values from demo/zcu104/gat_all_unsigned.hwh:16153-18563
     want = {"CTRL": 0x0, "gemm_mode": 0x58, "relu": 0x60, "gat_mode": 0x50, "scale_fea": 0x68, "max_fea": 0x70,
