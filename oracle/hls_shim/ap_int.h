@@ -34,6 +34,33 @@ template <int N> struct ap_uint {
     ap_uint &operator++() { ++v; return *this; }
 };
 
+/*  ap_fixed<16, 2> (the EIGHTBIT build's ATYPE / BTYPE / DTYPE / FTYPE / ITYPE, matrix_mult.h:105-109) with the
+ *  documented Vitis-HLS defaults: quantisation AP_TRN (truncate towards minus infinity) and overflow AP_WRAP.  Raw
+ *  two's-complement storage (Q2.14), so a buffer of int16 codes is a buffer of this type.  Only what the kernel source
+ *  uses: construction from 0 / numbers, product and sum assigned back to the same type, comparison with 0.
+ *  A full-precision product added to an accumulator and then truncated equals the truncated product added
+ *  (acc * 2^14 is a multiple of 2^14), so `acc += a * b` and `t = a * b; acc += t` agree, as in the real type. */
+template <int W, int I> struct ap_fixed {
+    static_assert(W == 16, "shim: 16-bit storage only");
+    int16_t v;
+    static int16_t wrap(long long r) { return (int16_t)(uint16_t)(unsigned long long)r; }
+    static long long floor_to_raw(double x) { double y = x * (double)(1 << (W - I)); long long r = (long long)y; if ((double)r > y) r--; return r; }
+    ap_fixed() {}
+    ap_fixed(int x) : v(wrap((long long)x * (1 << (W - I)))) {}
+    ap_fixed(long long x) : v(wrap(x * (1 << (W - I)))) {}
+    ap_fixed(double x) : v(wrap(floor_to_raw(x))) {}
+    ap_fixed(float x) : v(wrap(floor_to_raw((double)x))) {}
+    static ap_fixed raw(int16_t r) { ap_fixed f; f.v = r; return f; }
+    explicit operator double() const { return (double)v / (double)(1 << (W - I)); }
+    ap_fixed &operator+=(const ap_fixed &o) { v = wrap((long long)v + (long long)o.v); return *this; }
+};
+template <int W, int I> inline ap_fixed<W, I> operator*(const ap_fixed<W, I> &a, const ap_fixed<W, I> &b) {
+    return ap_fixed<W, I>::raw(ap_fixed<W, I>::wrap(((long long)a.v * (long long)b.v) >> (W - I)));   /* >> on a negative value: floor (AP_TRN) */
+}
+template <int W, int I> inline ap_fixed<W, I> operator+(const ap_fixed<W, I> &a, const ap_fixed<W, I> &b) { ap_fixed<W, I> r = a; r += b; return r; }
+template <int W, int I> inline bool operator>(const ap_fixed<W, I> &a, int z) { return (long long)a.v > (long long)z * (1 << (W - I)); }
+template <int W, int I> inline bool operator<(const ap_fixed<W, I> &a, int z) { return (long long)a.v < (long long)z * (1 << (W - I)); }
+
 #if defined(SGRACE_REF_ELT_FLOAT)
 typedef float half;
 #else

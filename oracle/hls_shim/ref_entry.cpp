@@ -4,7 +4,8 @@
  * TEST INFRASTRUCTURE ONLY: validates oracle/sgrace_oracle.c and can serve as the CPU
  * baseline ("kind": "reference").  Build-time configuration is whatever the reference's
  * matrix_mult.h fixes: HALF types, FADD latency 4, SPMM_BLOCK 1, 1 FEA / 1 ADJ thread,
- * B_WIDTH_BLOCK 2, caps MAX_N = MAX_M = 6144.
+ * B_WIDTH_BLOCK 2, caps MAX_N = MAX_M = 6144.  The fix16 build (ref_kernel_eightbit.cpp) selects the EIGHTBIT types
+ * (ap_fixed<16,2> stand-in, latency 1) instead.
  */
 #include <stdio.h>
 #include <stdlib.h>

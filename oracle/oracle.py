@@ -262,8 +262,9 @@ def ref_lib(kind="half"):
 
 
 def ref_layer(*, kind, N, M_fea, P, adj, B, fea=None, x_dense=None, relu=0):
-    """Call the reference's mmult_top.  kind='half' -> uint16 storage, 'float' -> float32."""
-    npdt = np.uint16 if kind == "half" else np.float32
+    """Call the reference's mmult_top.  kind='half' -> uint16 storage, 'float' -> float32, 'fix16' -> int16 Q2.14 codes
+    (the EIGHTBIT configuration of the source with the ap_fixed<16,2> stand-in of oracle/hls_shim/ap_int.h)."""
+    npdt = {"half": np.uint16, "fix16": np.int16}.get(kind, np.float32)
     L = ref_lib(kind)
     rp, ci, va = _c(adj[0], np.int32), _c(adj[1], np.int32), _c(adj[2], npdt)
     Bc = _c(B, npdt)

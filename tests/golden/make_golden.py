@@ -16,6 +16,7 @@ Writes into tests/golden/:
                       unmodified with tiny stand-ins for its unavailable imports
                       (torch_geometric, torch_scatter) and the reference's emulation config.py.
   sym_norm2.npz       inputs + outputs of the reference's sym_norm2 (sgrace.py:18-51)
+  ref_hls_fix16.npz   the same for the EIGHTBIT configuration (ap_fixed<16,2>): int16 codes, incl. a set that wraps around
   ref_hls_*.npz       outputs of the reference HLS source compiled natively (oracle/_ref) on
                       small seeded inputs, so the GPU box can check against the real kernel code
   real_mol.npz        the reference's own molecule matrices (data/matrices/mol_*.txt, main_float.cpp:40-51:
@@ -234,6 +235,40 @@ def ref_hls():
                                                    x_dense=O.to_storage(xd, dt), relu=1)
     np.savez_compressed(os.path.join(HERE, "ref_hls.npz"), **d)
     print("ref_hls.npz", sorted(k for k in d if "relu" in k))
+    ref_hls_fix16()
+
+
+def ref_hls_fix16():
+    """The same source in its EIGHTBIT configuration (ap_fixed<16,2>, latency 1; oracle/_ref/libsgrace_hlsref_fix16.so):
+    int16 Q2.14 outputs on seeded inputs, one set small enough to stay in range and one that wraps around."""
+    if not O.ref_available("fix16"):
+        print("oracle/_ref fix16 build missing; run `make -C oracle ref` first")
+        return
+    from sgracex1_b200 import graphs as G
+    d = {}
+    for tag, scale in (("small", 0.5), ("wrap", 3.0)):
+        rng = np.random.default_rng(21 if tag == "small" else 22)
+        p = G.cora_shape(seed=5, P=16, n=400, m=120, nnz_adj=2000, nnz_fea=3600)
+        av = (p.adj_val * scale * 2).astype(np.float32)
+        fv = rng.uniform(-scale, scale, size=len(p.fea_val)).astype(np.float32)
+        W = rng.uniform(-scale, scale, size=(p.M, 16)).astype(np.float32)
+        xd = ((rng.random((p.N, 24)) < 0.5) * rng.uniform(-scale, scale, size=(p.N, 24))).astype(np.float32)
+        wd = rng.uniform(-0.5, 0.5, size=(24, 10)).astype(np.float32)
+        adj = (p.adj_rowptr, p.adj_col, O.to_storage(av, O.FIX16))
+        fea = (p.fea_rowptr, p.fea_col, O.to_storage(fv, O.FIX16))
+        d.update({f"{tag}_N": p.N, f"{tag}_M": p.M, f"{tag}_adj_rowptr": p.adj_rowptr, f"{tag}_adj_col": p.adj_col,
+                  f"{tag}_adj_val": adj[2], f"{tag}_fea_rowptr": p.fea_rowptr, f"{tag}_fea_col": p.fea_col, f"{tag}_fea_val": fea[2],
+                  f"{tag}_x_dense": O.to_storage(xd, O.FIX16)})
+        for P in (16, 7):
+            B = O.to_storage(O.weights_to_B(W[:, :P]), O.FIX16)
+            d[f"{tag}_B_P{P}"] = B
+            for relu in (0, 1):
+                d[f"{tag}_sparse_P{P}_relu{relu}"] = O.ref_layer(kind="fix16", N=p.N, M_fea=p.M, P=P, adj=adj, B=B, fea=fea, relu=relu)
+        Bd = O.to_storage(O.weights_to_B(wd), O.FIX16)
+        d[f"{tag}_B_dense"] = Bd
+        d[f"{tag}_dense_P10_relu1"] = O.ref_layer(kind="fix16", N=p.N, M_fea=24, P=10, adj=adj, B=Bd, x_dense=d[f"{tag}_x_dense"], relu=1)
+    np.savez_compressed(os.path.join(HERE, "ref_hls_fix16.npz"), **d)
+    print("ref_hls_fix16.npz", sorted(k for k in d if "relu" in k))
 
 
 def _kinds():

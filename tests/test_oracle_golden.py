@@ -79,6 +79,49 @@ def test_reference_hls_fixtures_bit_exact():
         assert np.array_equal(D.view(np.uint8), g[f"{kind}_dense_P10_relu1"].view(np.uint8))
 
 
+def test_reference_hls_fix16_fixtures_bit_exact():
+    """FIX16 (ap_fixed<16,2>): the oracle against outputs of the reference's own source compiled in its EIGHTBIT
+    configuration (oracle/hls_shim/ref_kernel_eightbit.cpp) -- the dataflow and the order of operations are the
+    reference's, the arithmetic type is the stand-in of oracle/hls_shim/ap_int.h (AP_TRN / AP_WRAP, the documented
+    defaults; the Xilinx header is not available).  One set stays in range, one wraps around."""
+    g = np.load(os.path.join(U.GOLDEN, "ref_hls_fix16.npz"))
+    for tag in ("small", "wrap"):
+        N, M = int(g[f"{tag}_N"]), int(g[f"{tag}_M"])
+        adj = (g[f"{tag}_adj_rowptr"], g[f"{tag}_adj_col"], g[f"{tag}_adj_val"])
+        fea = (g[f"{tag}_fea_rowptr"], g[f"{tag}_fea_col"], g[f"{tag}_fea_val"])
+        for P in (16, 7):
+            for relu in (0, 1):
+                D = O.layer(dtype=O.FIX16, N=N, M_fea=M, P=P, adj=adj, fea=fea, B=g[f"{tag}_B_P{P}"], relu=relu, spmm_block=1,
+                            lat_fea=1, lat_adj=1)
+                assert np.array_equal(D, g[f"{tag}_sparse_P{P}_relu{relu}"]), (tag, P, relu)
+        D = O.layer(dtype=O.FIX16, N=N, M_fea=24, P=10, adj=adj, x_dense=g[f"{tag}_x_dense"], B=g[f"{tag}_B_dense"], relu=1,
+                    spmm_block=1, lat_fea=1, lat_adj=1)
+        assert np.array_equal(D, g[f"{tag}_dense_P10_relu1"]), tag
+    # the wrap-around set really wraps: its exact result leaves [-2, 2)
+    import scipy.sparse as sp
+    N, M = int(g["wrap_N"]), int(g["wrap_M"])
+    A = sp.csr_matrix((g["wrap_adj_val"].astype(np.float64) / 16384, g["wrap_adj_col"], g["wrap_adj_rowptr"]), shape=(N, N))
+    X = sp.csr_matrix((g["wrap_fea_val"].astype(np.float64) / 16384, g["wrap_fea_col"], g["wrap_fea_rowptr"]), shape=(N, M))
+    W = g["wrap_B_P16"].reshape(16, M).T.astype(np.float64) / 16384
+    assert (np.abs(A @ (X @ W)) >= 2).sum() > 0
+
+
+@pytest.mark.skipif(not O.ref_available("fix16"), reason="oracle/_ref EIGHTBIT build of the reference source not built")
+def test_against_compiled_reference_fix16():
+    for seed, scale in ((5, 0.5), (7, 1.5), (8, 3.0)):
+        pr = U.random_problem(seed, n=257, m=40, p=7, val_scale=scale)
+        a, f, B, xd = U.to_storage_problem(pr, O.FIX16)
+        for relu in (0, 1):
+            ref = O.ref_layer(kind="fix16", N=pr["N"], M_fea=pr["M"], P=pr["P"], adj=a, fea=f, B=B, relu=relu)
+            mine = O.layer(dtype=O.FIX16, N=pr["N"], M_fea=pr["M"], P=pr["P"], adj=a, fea=f, B=B, relu=relu, spmm_block=1,
+                           lat_fea=1, lat_adj=1)
+            assert np.array_equal(ref, mine)
+            ref = O.ref_layer(kind="fix16", N=pr["N"], M_fea=pr["M"], P=pr["P"], adj=a, x_dense=xd, B=B, relu=relu)
+            mine = O.layer(dtype=O.FIX16, N=pr["N"], M_fea=pr["M"], P=pr["P"], adj=a, x_dense=xd, B=B, relu=relu, spmm_block=1,
+                           lat_fea=1, lat_adj=1)
+            assert np.array_equal(ref, mine)
+
+
 @pytest.mark.skipif(not (O.ref_available("half") and O.ref_available("float")),
                     reason="oracle/_ref (reference HLS source compiled natively) not built")
 def test_against_compiled_reference_full_matrix():
