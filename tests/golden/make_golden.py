@@ -208,6 +208,44 @@ def qlayers():
     print("sym_norm2.npz", e2.shape)
 
 
+
+def backward_emulation():
+    """Software backward of FPYNQ_GAT (sgrace.py:880-1110, accb = 0) run by the imported reference: the tensors its
+    forward saved, a seeded grad_output and the three gradients it returns, GCN and GAT."""
+    rng = np.random.default_rng(7)
+    ei, x, w, att = small_graph(rng, 96, 40, 16)
+    n = x.shape[0]
+    d = {}
+    for gat in (0, 1):
+        config, sg = import_reference_sgrace(8, gat)
+        edge_index, norm = sg.sym_norm2(torch.from_numpy(ei), n, None, 1, torch.float32)
+        adj = torch.sparse_coo_tensor(edge_index, norm, (n, n))
+        layer = sg.GATConv_SGRACE(x.shape[1], w.shape[1], nheads=1, bias=False)
+        layer.weight.data = torch.from_numpy(w.copy())
+        layer.attention.data = torch.from_numpy(att.copy())
+        xt = torch.from_numpy(x.copy()).requires_grad_(True)
+        out = layer.forward(gat, 0, 1, xt, edge_index, norm, adj)
+        node = out.grad_fn
+        assert "FPYNQ_GAT" in type(node).__name__
+        saved = node.saved_tensors                      # adj, input, weights, e, attentions, output
+        names = ("adj", "input", "weights", "e", "attentions", "output")
+        for nm, t in zip(names, saved):
+            if nm == "adj":
+                continue
+            d[f"gat{gat}_{nm}"] = t.detach().to_dense().numpy().astype(np.float32) if t.is_sparse else t.detach().numpy().astype(np.float32)
+        g = torch.from_numpy(np.random.default_rng(11 + gat).standard_normal(tuple(out.shape)).astype(np.float32))
+        out.backward(g)
+        d[f"gat{gat}_grad_output"] = g.numpy()
+        d[f"gat{gat}_grad_input"] = xt.grad.numpy().astype(np.float32)
+        d[f"gat{gat}_grad_weights"] = layer.weight.grad.numpy().astype(np.float32)
+        d[f"gat{gat}_grad_attention"] = layer.attention.grad.numpy().astype(np.float32)
+        d[f"gat{gat}_alpha"] = np.float32(node.alpha) if hasattr(node, "alpha") else np.float32(0.2)
+        d["edge_index"] = edge_index.numpy().astype(np.int32)
+        d["norm"] = norm.numpy().astype(np.float32)
+    d["n"] = n
+    np.savez_compressed(os.path.join(HERE, "backward_emulation.npz"), **d)
+    print("backward_emulation.npz", {k: v.shape for k, v in d.items() if hasattr(v, "shape") and "grad" in k})
+
 def ref_hls():
     """Outputs of the reference HLS kernel source (compiled in oracle/_ref) on seeded inputs."""
     if not (O.ref_available("half") and O.ref_available("float")):
@@ -432,6 +470,7 @@ if __name__ == "__main__":
     citeseer()
     toy()
     ref_hls()
+    backward_emulation()
     real_files()
     demo_model()
     qlayers()

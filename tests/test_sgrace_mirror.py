@@ -79,3 +79,30 @@ def test_gatconv_sgrace_against_reference_emulation(qbits, gat):
         assert S.cur_max_fea > 0
     finally:
         S.free_SGRACE()
+
+
+@pytest.mark.parametrize("gat", [0, 1])
+def test_software_backward_matches_the_reference_emulation(gat):
+    """FPYNQ_GAT.backward with accb = 0 (sgrace.py:880-1110): the tensors the reference's forward saved and a seeded
+    grad_output go through the mirror's backward; grad_input, grad_weights and the attention gradient equal the ones the
+    imported reference returned (tests/golden/make_golden.py:backward_emulation).  CPU only: this is host code."""
+    import types
+    from sgracex1_b200 import config, sgrace as S
+    g = np.load(os.path.join(U.GOLDEN, "backward_emulation.npz"))
+    n = int(g["n"])
+    adj = torch.sparse_coo_tensor(torch.from_numpy(g["edge_index"].astype(np.int64)), torch.from_numpy(g["norm"]), (n, n))
+    t = lambda k: torch.from_numpy(g[f"gat{gat}_{k}"])
+    ctx = types.SimpleNamespace(saved_tensors=(adj, t("input"), t("weights"), t("e"), t("attentions"), t("output")),
+                                alpha=float(g[f"gat{gat}_alpha"]), nheads=1)
+    old = (config.accb, config.compute_attention)
+    config.accb, config.compute_attention = 0, gat
+    try:
+        grads = S.FPYNQ_GAT.backward(ctx, t("grad_output"))
+    finally:
+        config.accb, config.compute_attention = old
+    grad_input, grad_weights, grad_attention = grads[4], grads[5], grads[6]
+    for name, got in (("grad_input", grad_input), ("grad_weights", grad_weights), ("grad_attention", grad_attention)):
+        want = g[f"gat{gat}_{name}"]
+        got = got.detach().numpy().reshape(want.shape)
+        scale = max(float(np.abs(want).max()), 1e-30)
+        assert np.abs(got - want).max() <= 1e-5 * scale, (name, float(np.abs(got - want).max()), scale)
