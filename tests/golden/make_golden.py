@@ -16,6 +16,8 @@ Writes into tests/golden/:
                       unmodified with tiny stand-ins for its unavailable imports
                       (torch_geometric, torch_scatter) and the reference's emulation config.py.
   sym_norm2.npz       inputs + outputs of the reference's sym_norm2 (sgrace.py:18-51)
+  backward_emulation.npz  saved tensors, grad_output and the three gradients of the reference's software backward
+                      (FPYNQ_GAT.backward, accb = 0), GCN and GAT, from the imported sgrace.py
   ref_hls_fix16.npz   the same for the EIGHTBIT configuration (ap_fixed<16,2>): int16 codes, incl. a set that wraps around
   ref_hls_*.npz       outputs of the reference HLS source compiled natively (oracle/_ref) on
                       small seeded inputs, so the GPU box can check against the real kernel code
